@@ -1,0 +1,121 @@
+/*
+ * mccnn_b200.h -- C ABI of libmccnn_b200.so: the Monte-Carlo-convolution forward path of viscom-ulm/MCCNN
+ * as sm_100a CUDA kernels.
+ *
+ * Every entry point replaces one host launcher of the reference (the C++-linkage functions its TensorFlow glue
+ * declares `extern` and calls from OpKernel::Compute); the replaced declaration is cited per function as
+ * tf_ops/<file>.cc:<line> (declaration) and tf_ops/<file>.cu:<line> (definition).
+ *
+ * Conventions (they differ from the reference where the reference blocks the host):
+ *   - plain pointers and sizes only; every pointer is DEVICE memory unless the name starts with `host`;
+ *     the caller owns all memory (outputs and workspaces) -- nothing is allocated inside;
+ *   - `void* stream` is a cudaStream_t; all work is enqueued on it, no entry point synchronises except
+ *     mc_determine_num_cells in the non-scale-invariant case;
+ *   - dynamic extents are passed as a pair (capacity, dCount): `capacity` is a host int bounding the extent,
+ *     `dCount` an optional device int holding the live extent (NULL: live extent == capacity).  Dynamic RESULTS
+ *     (number of neighbours, number of Poisson samples) are written to device ints, never returned to the host;
+ *   - all tensors are dense row-major float32 / int32 exactly as the reference's ops lay them out
+ *     (points [N,3], batch ids [N], cell table [B,n,n,n,2], neighbour list start[M] + pairs[K,2] = (j, i));
+ *   - return value: 0 ok, 1 invalid argument, 2 CUDA error; mc_last_error() gives the message.
+ */
+#ifndef MCCNN_B200_H_
+#define MCCNN_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* mc_last_error(void);
+int mc_abi_version(void);
+/* BLOCK_MLP_SIZE of the build == python get_block_size() (tf_ops/genCompileScript.py:20,46-47) */
+int mc_get_block_size(void);
+int mc_device_info(int* hostSmCount, int* hostCcMajor, int* hostCcMinor);
+
+/* computeAABB -- tf_ops/aabb_gpu.cc:38-40, tf_ops/aabb_gpu.cu:121-141.  workspace: 1 int. */
+int mc_compute_aabb(int scaleInv, int numPoints, int batchSize, const float* pts, const int* batchIds,
+                    float* aabbMin, float* aabbMax, int* workspace, void* stream);
+
+/* determineNumCells -- tf_ops/sort_gpu.cc:105-110, tf_ops/sort_gpu.cu:397-420.  workspace: 1 int (scaleInv == 0). */
+int mc_determine_num_cells(int scaleInv, float cellSize, const float* aabbMin, const float* aabbMax, int* workspace,
+                           int* hostOutNumCells, void* stream);
+
+/* computeAuxiliarBuffersSize(int,int,int*,int*,int*) -- tf_ops/sort_gpu.cc:112-117, tf_ops/sort_gpu.cu:422-434 */
+long long mc_sort_step1_workspace_ints(int numPoints, int batchSize, int numCells);
+
+/* sortPointsStep1GPUKernel -- tf_ops/sort_gpu.cc:119-131, tf_ops/sort_gpu.cu:436-471 */
+int mc_sort_points_step1(int numPoints, const int* dNumPoints, int batchSize, int numCells, const float* aabbMin,
+                         const float* aabbMax, const float* pts, const int* batchIds, int* workspace, int* keys,
+                         int* newIdx, void* stream);
+
+/* sortPointsStep2GPUKernel -- tf_ops/sort_gpu.cc:133-147, tf_ops/sort_gpu.cu:473-497.  workspace: numPoints ints. */
+int mc_sort_points_step2(int numPoints, const int* dNumPoints, int batchSize, int numFeatures, int numCells,
+                         const float* pts, const int* batchIds, const float* features, const int* keys,
+                         const int* newIdx, int* workspace, float* outPts, int* outBatchIds, float* outFeatures,
+                         int* outCellIdx, void* stream);
+
+/* sortFeaturesBackGrad (python sort_features) -- tf_ops/sort_gpu.cc:165-170, tf_ops/sort_gpu.cu:529-540 */
+int mc_sort_features(int numPoints, const int* dNumPoints, int numFeatures, const float* in, const int* newIdx,
+                     float* out, void* stream);
+
+/* sortFeaturesBack -- tf_ops/sort_gpu.cc:158-163, tf_ops/sort_gpu.cu:516-527 */
+int mc_sort_features_back(int numPoints, const int* dNumPoints, int numFeatures, const float* in, const int* newIdx,
+                          float* out, void* stream);
+
+/* computeInverseIndexs + transformIndexs -- tf_ops/sort_gpu.cc:172-182, tf_ops/sort_gpu.cu:542-564.
+ * workspace: numPoints ints. */
+int mc_transform_indexs(int numIndexs, const int* dNumIndexs, int numPoints, const int* dNumPoints,
+                        const int* inIndexs, const int* newIdx, int* workspace, int* out, void* stream);
+
+/* computeAuxiliarBuffersSize(int,int*,int*) -- tf_ops/find_neighbors.cc:58-61, tf_ops/find_neighbors.cu:319-328 */
+long long mc_find_neighbors_workspace_ints(int numSamples);
+
+/* countNeighborsCPU -- tf_ops/find_neighbors.cc:45-56, tf_ops/find_neighbors.cu:268-317.
+ * The total is written to *dNumNeighbors (device) instead of being returned through a blocking copy. */
+int mc_find_neighbors_count(int scaleInv, int numSamples, const int* dNumSamples, int numCells, float radius,
+                            const float* samples, const int* sampleBatchIds, const float* pts2, const int* cellIdx,
+                            const float* aabbMin, const float* aabbMax, int* startIdx, int* workspace,
+                            int* dNumNeighbors, void* stream);
+
+/* packNeighborsCPU -- tf_ops/find_neighbors.cc:63-78, tf_ops/find_neighbors.cu:330-371.
+ * Same startIdx / workspace as the count call.  *dOverflow (optional) is set when capacityPairs is exceeded. */
+int mc_find_neighbors_pack(int scaleInv, int numSamples, const int* dNumSamples, int numCells, float radius,
+                           const float* samples, const int* sampleBatchIds, const float* pts2, const int* cellIdx,
+                           const float* aabbMin, const float* aabbMax, int* startIdx, const int* workspace,
+                           int* pairs, int capacityPairs, int* dOverflow, void* stream);
+
+/* computeDPFsCPU -- tf_ops/compute_pdf.cc:43-55, tf_ops/compute_pdf.cu:98-120 */
+int mc_compute_pdf(int scaleInv, float window, int numSamples, const int* dNumSamples, int numNeighbors,
+                   const int* dNumNeighbors, float radius, const float* pts, const int* batchIds,
+                   const float* aabbMin, const float* aabbMax, const int* startIdx, const int* pairs, float* pdfs,
+                   void* stream);
+
+long long mc_poisson_workspace_ints(int numPoints, int batchSize);
+
+/* samplePointCloud + copyPoints -- tf_ops/poisson_sampling.cc:68-92, tf_ops/poisson_sampling.cu:175-244.
+ * Outputs hold capacityOut rows (numPoints always suffices); the number of samples is written to *dNumSamples
+ * (device); *dOverflow (optional) is set when it exceeds capacityOut. */
+int mc_poisson_sampling(int scaleInv, float radius, int numPoints, const int* dNumPoints, int batchSize,
+                        int numCells, const float* aabbMin, const float* aabbMax, const float* pts,
+                        const int* batchIds, const int* cellIdx, int* workspace, int capacityOut, float* outPts,
+                        int* outBatchIds, int* outIdx, int* dNumSamples, int* dOverflow, void* stream);
+
+/* getFeaturesSampledPoints -- tf_ops/poisson_sampling.cc:94-100, tf_ops/poisson_sampling.cu:246-258 */
+int mc_get_sampled_features(int numSamples, const int* dNumSamples, int numFeatures, const int* idx,
+                            const float* features, float* out, void* stream);
+
+long long mc_spatial_conv_workspace_floats(int numSamples, int numInFeatures, int numOutFeatures, int combin);
+
+/* spatialConvCPU -- tf_ops/spatial_conv.cc:98-128, tf_ops/spatial_conv.cu:796-871.
+ * Parameter order is the op's (W1, b1, W2, b2, Wout, bout); buffers are the flat layouts the reference kernel
+ * indexes (tf_ops/spatial_conv.cu:49-73,172). */
+int mc_spatial_conv(int avg, int scaleInv, int numNeighbors, const int* dNumNeighbors, int numInFeatures,
+                    int numOutFeatures, int numSamples, const int* dNumSamples, int combin, float radius,
+                    const float* pts, const int* batchIds, const float* features, const float* pdfs,
+                    const float* samples, const int* startIdx, const int* pairs, const float* aabbMin,
+                    const float* aabbMax, const float* W1, const float* b1, const float* W2, const float* b2,
+                    const float* Wout, const float* bout, float* workspace, float* outFeatures, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCCNN_B200_H_ */

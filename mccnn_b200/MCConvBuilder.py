@@ -1,0 +1,188 @@
+"""PointHierarchy and ConvolutionBuilder -- the interface the reference's models are written against
+(utils/MCConvBuilder.py:24-131 and :133-427), re-hosted on torch CUDA tensors and the sm_100a op library.
+
+Same constructor / create_convolution / reset signatures, attribute names (points_, features_, batchIds_,
+sampledIndexs_, radiusList_, batchSize_, relativeRadius_, hierarchyName_, aabbMin_, aabbMax_, cacheGrids_, cacheNeighs_,
+cachePDFs_), cache-key scheme (utils/MCConvBuilder.py:230-238), variable names and shapes
+(<conv>_weights [3, 8nb], _biases [8nb], _weights2 / _weights3 [nb, 8, 8] -> reshaped WITHOUT transpose to [8, 8nb],
+_biases2 / _biases3 [nb, 8] -> [8nb]; utils/MCConvBuilder.py:397-419) and error behaviour (RuntimeError on mismatched
+batch sizes / feature counts, :326-333).  Variables live in a mccnn_b200.variables.VariableStore instead of the
+TensorFlow graph.
+
+Both classes work unchanged inside mccnn_b200.runtime.record()/planned(): the op wrappers they call carry the live
+row counts on the device, so a planned run issues no host synchronisation at all.
+"""
+import torch
+
+from .MCConvModule import (compute_aabb, sort_points_step1, sort_points_step2, sort_features, sort_features_back,
+                           compute_pdf, poisson_sampling, get_sampled_features, spatial_conv, get_block_size,
+                           transform_indexs, find_neighbors)
+from . import runtime as _rt
+from . import variables as _vars
+
+VERBOSE = False
+
+
+def _log(msg):
+    if VERBOSE:
+        print(msg)
+
+
+class PointHierarchy:
+    """Poisson-disk point hierarchy of a packed batch (utils/MCConvBuilder.py:24-131).
+
+    Level 0 is the input cloud; level l+1 is the Poisson-disk sampling of level l with radiusList[l].  The bounding
+    boxes are computed once on level 0 and reused for every level (utils/MCConvBuilder.py:85-88)."""
+
+    def __init__(self, inPoints, inFeatures, inBatchIds, radiusList, hierarchyName="Point_Hierarchy", batchSize=32,
+                 relativeRadius=True):
+        self.points_ = [inPoints]
+        self.features_ = [inFeatures]
+        self.batchIds_ = [inBatchIds]
+        self.sampledIndexs_ = []
+        self.radiusList_ = [0.0]
+        self.batchSize_ = batchSize
+        self.relativeRadius_ = relativeRadius
+        self.hierarchyName_ = hierarchyName
+
+        aabbMin, aabbMax = compute_aabb(inPoints, inBatchIds, batchSize, self.relativeRadius_)
+        self.aabbMin_ = aabbMin
+        self.aabbMax_ = aabbMax
+
+        _log("########## Point Hierarchy: " + hierarchyName + " (Rel: " + str(relativeRadius) + ")")
+        currPts, currFeatures, currBatchIds = inPoints, inFeatures, inBatchIds
+        for level, currRadius in enumerate(radiusList):
+            _log("Level: " + str(level + 1) + " | Poisson Disk Radius: " + str(currRadius))
+            keys, indexs = sort_points_step1(currPts, currBatchIds, self.aabbMin_, self.aabbMax_, self.batchSize_,
+                                             currRadius, self.relativeRadius_)
+            sortPts, sortBatchs, sortFeatures, cellIndexs = sort_points_step2(
+                currPts, currBatchIds, currFeatures, keys, indexs, self.aabbMin_, self.aabbMax_, self.batchSize_,
+                currRadius, self.relativeRadius_)
+            sampledPts, sampledBatchsIds, sampledIndexs = poisson_sampling(
+                sortPts, sortBatchs, cellIndexs, aabbMin, aabbMax, currRadius, batchSize, self.relativeRadius_)
+            sampledFeatures = get_sampled_features(sampledIndexs, sortFeatures)
+            transformedIndexs = transform_indexs(sampledIndexs, indexs)
+
+            self.points_.append(sampledPts)
+            self.batchIds_.append(sampledBatchsIds)
+            self.features_.append(sampledFeatures)
+            self.sampledIndexs_.append(transformedIndexs)
+            self.radiusList_.append(currRadius)
+            currPts, currBatchIds, currFeatures = sampledPts, sampledBatchsIds, sampledFeatures
+
+
+class ConvolutionBuilder:
+    """Creates Monte-Carlo convolutions on point hierarchies, caching grids / neighbour lists / pdfs
+    (utils/MCConvBuilder.py:133-427)."""
+
+    def __init__(self, multiFeatureConvs=False, KDEWindow=0.25, relativeRadius=True, usePDF=True, useAVG=True,
+                 decayLossCollection='weight_decay_loss', variableStore=None):
+        self.cacheGrids_ = {}
+        self.cacheNeighs_ = {}
+        self.cachePDFs_ = {}
+        self.multiFeatureConvs_ = multiFeatureConvs
+        self.KDEWindow_ = KDEWindow
+        self.relativeRadius_ = relativeRadius
+        self.usePDF_ = usePDF
+        self.useAVG_ = useAVG
+        self.decayLossCollection_ = decayLossCollection
+        self.variables_ = variableStore if variableStore is not None else _vars.default_store()
+
+    def __compute_dic_keys__(self, inPointHierarchy, outPointHierarchy, inPointLevel, outPointLevel, convRadius,
+                             KDEWindow, relativeRadius, usePDF):
+        keyGrid = inPointHierarchy.hierarchyName_ + '|' + str(inPointLevel) + '|' + str(convRadius) + '|' + \
+            str(relativeRadius)
+        keyNeighs = keyGrid + '|' + outPointHierarchy.hierarchyName_ + '|' + str(outPointLevel)
+        keyPDF = keyNeighs + '|' + str(KDEWindow) + '|' + str(usePDF)
+        return keyGrid, keyNeighs, keyPDF
+
+    def reset(self):
+        self.cacheGrids_ = {}
+        self.cacheNeighs_ = {}
+        self.cachePDFs_ = {}
+
+    def create_convolution(self, convName, inPointHierarchy, inPointLevel, inFeatures, inNumFeatures, convRadius,
+                           outPointHierarchy=None, outPointLevel=None, multiFeatureConv=None, outNumFeatures=None,
+                           KDEWindow=None, relativeRadius=None, usePDF=None, useAVG=None):
+        currMultiFeatureConv = self.multiFeatureConvs_ if multiFeatureConv is None else multiFeatureConv
+        currNumOutFeatures = inNumFeatures if outNumFeatures is None else outNumFeatures
+        currKDEWindow = self.KDEWindow_ if KDEWindow is None else KDEWindow
+        currRelativeRadius = self.relativeRadius_ if relativeRadius is None else relativeRadius
+        currUsePDF = self.usePDF_ if usePDF is None else usePDF
+        currUseAVG = self.useAVG_ if useAVG is None else useAVG
+        currOutPointHierarchy = inPointHierarchy if outPointHierarchy is None else outPointHierarchy
+        currOutPointLevel = inPointLevel if outPointLevel is None else outPointLevel
+
+        if currOutPointHierarchy.batchSize_ != inPointHierarchy.batchSize_:
+            raise RuntimeError('Different batch size in the input and output point hierarchy')
+        if (currMultiFeatureConv is False) and (currNumOutFeatures != inNumFeatures):
+            raise RuntimeError('The number of input and output features should be the same '
+                               'for multi feature convolutions.')
+
+        keyGrid, keyNeighs, keyPDF = self.__compute_dic_keys__(
+            inPointHierarchy, currOutPointHierarchy, inPointLevel, currOutPointLevel, convRadius, currKDEWindow,
+            currRelativeRadius, currUsePDF)
+        _log("Convolution: " + str(convName) + " (KDE: " + str(currKDEWindow) + " | MF: " + str(currMultiFeatureConv) +
+             " | Rel: " + str(currRelativeRadius) + " | PDF: " + str(currUsePDF) + ")")
+
+        ph = inPointHierarchy
+        # grid: cache hit -> only re-sort the new features into the cached order (utils/MCConvBuilder.py:349-351)
+        if keyGrid in self.cacheGrids_:
+            currGridTuple = self.cacheGrids_[keyGrid]
+            sortFeatures = sort_features(inFeatures, currGridTuple[3])
+        else:
+            keys, indexs = sort_points_step1(ph.points_[inPointLevel], ph.batchIds_[inPointLevel], ph.aabbMin_,
+                                             ph.aabbMax_, ph.batchSize_, convRadius, currRelativeRadius)
+            sortPts, sortBatchs, sortFeatures, cellIndexs = sort_points_step2(
+                ph.points_[inPointLevel], ph.batchIds_[inPointLevel], inFeatures, keys, indexs, ph.aabbMin_,
+                ph.aabbMax_, ph.batchSize_, convRadius, currRelativeRadius)
+            currGridTuple = (sortPts, sortBatchs, cellIndexs, indexs)
+            self.cacheGrids_[keyGrid] = currGridTuple
+
+        if keyNeighs in self.cacheNeighs_:
+            currNeighTuple = self.cacheNeighs_[keyNeighs]
+        else:
+            startIndexs, packedNeighs = find_neighbors(
+                currOutPointHierarchy.points_[currOutPointLevel], currOutPointHierarchy.batchIds_[currOutPointLevel],
+                currGridTuple[0], currGridTuple[2], ph.aabbMin_, ph.aabbMax_, convRadius, ph.batchSize_,
+                currRelativeRadius)
+            currNeighTuple = (startIndexs, packedNeighs)
+            self.cacheNeighs_[keyNeighs] = currNeighTuple
+
+        if keyPDF in self.cachePDFs_:
+            currPDFs = self.cachePDFs_[keyPDF]
+        else:
+            if currUsePDF:
+                currPDFs = compute_pdf(currGridTuple[0], currGridTuple[1], ph.aabbMin_, ph.aabbMax_,
+                                       currNeighTuple[0], currNeighTuple[1], currKDEWindow, convRadius,
+                                       ph.batchSize_, currRelativeRadius)
+            else:  # tf.ones([K, 1]) (utils/MCConvBuilder.py:388-390)
+                neigh = currNeighTuple[1]
+                currPDFs = _rt.tag(torch.ones((neigh.shape[0], 1), dtype=torch.float32, device=neigh.device),
+                                   _rt.count_of(neigh))
+            self.cachePDFs_[keyPDF] = currPDFs
+
+        # parameters (utils/MCConvBuilder.py:394-419)
+        vs = self.variables_
+        blockSize = get_block_size()
+        numOutNeurons = inNumFeatures * currNumOutFeatures if currMultiFeatureConv else inNumFeatures
+        numBlocks = int(numOutNeurons / blockSize)
+        if numOutNeurons % blockSize != 0:
+            numBlocks = numBlocks + 1
+        weights = vs.get_variable(convName + '_weights', [3, blockSize * numBlocks], "glorot")
+        vs.add_to_collection(self.decayLossCollection_, weights)
+        biases = vs.get_variable(convName + '_biases', [blockSize * numBlocks], "zeros")
+        weights2 = vs.get_variable(convName + '_weights2', [numBlocks, blockSize, blockSize], "glorot")
+        weights2 = weights2.reshape(blockSize, numBlocks * blockSize)
+        vs.add_to_collection(self.decayLossCollection_, weights2)
+        biases2 = vs.get_variable(convName + '_biases2', [numBlocks, blockSize], "zeros").reshape(numBlocks * blockSize)
+        weights3 = vs.get_variable(convName + '_weights3', [numBlocks, blockSize, blockSize], "glorot")
+        weights3 = weights3.reshape(blockSize, numBlocks * blockSize)
+        vs.add_to_collection(self.decayLossCollection_, weights3)
+        biases3 = vs.get_variable(convName + '_biases3', [numBlocks, blockSize], "zeros").reshape(numBlocks * blockSize)
+
+        return spatial_conv(currGridTuple[0], sortFeatures, currGridTuple[1], currPDFs,
+                            currOutPointHierarchy.points_[currOutPointLevel], currNeighTuple[0], currNeighTuple[1],
+                            ph.aabbMin_, ph.aabbMax_, weights, weights2, weights3, biases, biases2, biases3,
+                            currNumOutFeatures, currMultiFeatureConv, ph.batchSize_, convRadius, currRelativeRadius,
+                            currUseAVG)

@@ -1,0 +1,232 @@
+"""The reference's Python op API (tf_ops/MCConvModuleSrc:20-73 + get_block_size, tf_ops/genCompileScript.py:46-47)
+on torch CUDA tensors, backed by libmccnn_b200.so.
+
+Same function names, argument order (including the two re-orderings the reference does between the Python wrapper
+and the op: compute_pdf MCConvModuleSrc:55-56, spatial_conv MCConvModuleSrc:70-73) and tensor shapes/dtypes as the
+TensorFlow ops (tf_ops/*.cc REGISTER_OP blocks): batch ids int32 [N,1], start indices int32 [M,1], pdfs float32
+[K,1], neighbour list int32 [K,2], cell table int32 [B,n,n,n,2], Poisson indices int32 [M].  Shape / attribute
+violations raise ValueError where the reference's glue raises InvalidArgument (OP_REQUIRES).
+
+These wrappers return exactly-shaped tensors, so find_neighbors and poisson_sampling read one int from the device
+(the reference blocks on the same counts: find_neighbors.cu:308, poisson_sampling.cu:222).  Inside
+`mccnn_b200.runtime.planned(plan)` the same functions return capacity-sized tensors whose live row count stays on the
+device (`tensor._mc_count`) and never block -- see mccnn_b200/runtime.py.
+"""
+import torch
+
+from . import ops
+from . import runtime as _rt
+from .runtime import count_of as _cnt, tag as _tag
+
+__all__ = ["compute_aabb", "sort_points_step1", "sort_points_step2", "sort_features", "sort_features_back",
+           "transform_indexs", "find_neighbors", "compute_pdf", "poisson_sampling", "get_sampled_features",
+           "spatial_conv", "get_block_size"]
+
+
+def _req(cond, msg):
+    if not cond:
+        raise ValueError(msg)
+
+
+def _check_points(t, name):
+    _req(t.dim() == 2 and t.shape[1] >= 3, name + " expects points with at least three components")
+
+
+def _check_bids(b, n, name):
+    _req(b.dim() == 2 and b.shape[1] == 1 and b.shape[0] == n, name + " expects batch ids of shape (numPoints, 1)")
+
+
+def _check_aabb(mn, mx, batch_size, name):
+    _req(mn.dim() == 2 and tuple(mn.shape) == (batch_size, 3), name + " expects an aabb min of shape (batchSize, 3)")
+    _req(mx.dim() == 2 and tuple(mx.shape) == (batch_size, 3), name + " expects an aabb max of shape (batchSize, 3)")
+
+
+def get_block_size():
+    return ops.get_block_size()
+
+
+def compute_aabb(inPts, inBatchIds, batchSize, scaleInv=True):
+    """ComputeAabb, tf_ops/aabb_gpu.cc:22-84 -> (aabbMin [B,3], aabbMax [B,3])."""
+    _req(batchSize > 0, "ComputeAabb expects a positive batch size")
+    _check_points(inPts, "ComputeAabb")
+    _check_bids(inBatchIds, inPts.shape[0], "ComputeAabb")
+    pts = inPts if inPts.shape[1] == 3 else inPts[:, :3]  # the kernel hard-codes stride 3 (aabb_gpu.cu:86)
+    return ops.compute_aabb(pts, inBatchIds.reshape(-1), batchSize, scaleInv)
+
+
+def _num_cells(aabbMin, aabbMax, cellSize, scaleInv):
+    _req(cellSize > 0.0, "expects a positive cell size")
+    return ops.num_cells(cellSize, scaleInv, aabbMin, aabbMax)
+
+
+def sort_points_step1(inPts, inBatchIds, aabbMin, aabbMax, batchSize, cellSize, scaleInv):
+    """SortPointsStep1, tf_ops/sort_gpu.cc:23-38,184-268 -> (keys [N], indexs [N])."""
+    _req(batchSize > 0, "SortPointsStep1 expects a positive batch size")
+    _req(inPts.dim() == 2 and inPts.shape[1] == 3, "SortPointsStep1 expects points with three components")
+    _check_bids(inBatchIds, inPts.shape[0], "SortPointsStep1")
+    _check_aabb(aabbMin, aabbMax, batchSize, "SortPointsStep1")
+    n = _num_cells(aabbMin, aabbMax, cellSize, scaleInv)
+    nd = _cnt(inPts)
+    keys, idx = ops.sort_points_step1(inPts, inBatchIds.reshape(-1), aabbMin, aabbMax, batchSize, n, nd)
+    return _tag(keys, nd), _tag(idx, nd)
+
+
+def sort_points_step2(inPts, inBatchIds, inFeatures, keys, indexs, aabbMin, aabbMax, batchSize, cellSize, scaleInv):
+    """SortPointsStep2, tf_ops/sort_gpu.cc:40-64,270-378 -> (pts [N,3], batchIds [N,1], features [N,C], cellIndexs)."""
+    _req(batchSize > 0, "SortPointsStep2 expects a positive batch size")
+    _req(inPts.dim() == 2 and inPts.shape[1] == 3, "SortPointsStep2 expects points with three components")
+    N = inPts.shape[0]
+    _check_bids(inBatchIds, N, "SortPointsStep2")
+    _req(inFeatures.dim() == 2 and inFeatures.shape[0] == N, "SortPointsStep2 expects features of shape (numPoints, C)")
+    _req(keys.dim() == 1 and keys.shape[0] == N, "SortPointsStep2 expects keys of shape (numPoints)")
+    _req(indexs.dim() == 1 and indexs.shape[0] == N, "SortPointsStep2 expects indexs of shape (numPoints)")
+    _check_aabb(aabbMin, aabbMax, batchSize, "SortPointsStep2")
+    n = _num_cells(aabbMin, aabbMax, cellSize, scaleInv)
+    nd = _cnt(inPts)
+    p, b, f, cells = ops.sort_points_step2(inPts, inBatchIds.reshape(-1), inFeatures, keys, indexs, batchSize, n, nd)
+    return _tag(p, nd), _tag(b.reshape(-1, 1), nd), _tag(f, nd), cells
+
+
+def sort_features(inFeatures, indexs):
+    """python sort_features -> SortFeaturesBackGrad op (MCConvModuleSrc:35-36): out[indexs[i]] = inFeatures[i]."""
+    _req(inFeatures.dim() == 2, "SortFeaturesBackGrad expects features of shape (numPoints, C)")
+    _req(indexs.dim() == 1 and indexs.shape[0] == inFeatures.shape[0],
+         "SortFeaturesBackGrad expects indexs of shape (numPoints)")
+    return _tag(ops.sort_features(inFeatures, indexs, _cnt(indexs)), _cnt(indexs))
+
+
+def sort_features_back(inFeatures, indexs):
+    """SortFeaturesBack, tf_ops/sort_gpu.cc:78-85: out[i] = inFeatures[indexs[i]]."""
+    _req(inFeatures.dim() == 2, "SortFeaturesBack expects features of shape (numPoints, C)")
+    _req(indexs.dim() == 1 and indexs.shape[0] == inFeatures.shape[0],
+         "SortFeaturesBack expects indexs of shape (numPoints)")
+    return _tag(ops.sort_features_back(inFeatures, indexs, _cnt(indexs)), _cnt(indexs))
+
+
+def transform_indexs(inIndexs, inNewPositions):
+    """TransformIndexs, tf_ops/sort_gpu.cc:96-103,496-533."""
+    _req(inIndexs.dim() == 1 and inNewPositions.dim() == 1, "TransformIndexs expects one-dimensional index tensors")
+    md = _cnt(inIndexs)
+    return _tag(ops.transform_indexs(inIndexs, inNewPositions, md, _cnt(inNewPositions)), md)
+
+
+def find_neighbors(inPts, inBatchIds, inPts2, cellIndexs, aabbMin, aabbMax, radius, batchSize, scaleInv):
+    """FindNeighbors, tf_ops/find_neighbors.cc:25-43,93-185 -> (startIndexs [M,1], neighIndexs [K,2])."""
+    _req(radius > 0.0, "FindNeighborsOp expects a positive radius")
+    _req(batchSize > 0, "FindNeighborsOp expects a positive batch size")
+    _req(inPts.dim() == 2 and inPts.shape[1] == 3, "FindNeighborsOp expects points with three components")
+    _check_bids(inBatchIds, inPts.shape[0], "FindNeighborsOp")
+    _req(inPts2.dim() == 2 and inPts2.shape[1] == 3, "FindNeighborsOp expects points with three components")
+    _req(cellIndexs.dim() == 5 and cellIndexs.shape[0] == batchSize,
+         "FindNeighborsOp expects a five dimension tensor for the cell indices")
+    _check_aabb(aabbMin, aabbMax, batchSize, "FindNeighborsOp")
+    bids = inBatchIds.reshape(-1)
+    md = _cnt(inPts)
+    start, ws, k_dev = ops.find_neighbors_count(inPts, bids, inPts2, cellIndexs, aabbMin, aabbMax, radius, scaleInv,
+                                                md)
+    if _rt.mode() == "planned":  # capacity-sized pair list, live K stays on the device
+        plan = _rt.current_plan()
+        pairs = ops.find_neighbors_pack(inPts, bids, inPts2, cellIndexs, aabbMin, aabbMax, radius, scaleInv, start,
+                                        ws, plan.next_capacity(), md, plan.overflow)
+        return _tag(start.reshape(-1, 1), md), _tag(pairs, k_dev)
+    K = int(k_dev.item())  # the one host sync of this op (the reference has the same one)
+    if _rt.mode() == "record":
+        _rt.current_plan().sizes.append(K)
+    pairs = ops.find_neighbors_pack(inPts, bids, inPts2, cellIndexs, aabbMin, aabbMax, radius, scaleInv, start, ws,
+                                    K, md)
+    return start.reshape(-1, 1), pairs
+
+
+def compute_pdf(inPts, inBatchIds, aabbMin, aabbMax, startIndexs, neighbors, window, radius, batchSize, scaleInv):
+    """ComputePDF, tf_ops/compute_pdf.cc:25-41,57-142 -> pdfs [K,1]."""
+    _req(window > 0.0, "ComputePDFOp expects a positive window")
+    _req(radius > 0.0, "ComputePDFOp expects a positive radius")
+    _req(batchSize > 0, "ComputePDFOp expects a positive batch size")
+    _req(inPts.dim() == 2 and inPts.shape[1] == 3, "ComputePDFOp expects points with three components")
+    _check_bids(inBatchIds, inPts.shape[0], "ComputePDFOp")
+    _req(startIndexs.dim() == 2 and startIndexs.shape[1] == 1, "ComputePDFOp expects start indexs of shape (M, 1)")
+    _req(neighbors.dim() == 2 and neighbors.shape[1] == 2, "ComputePDFOp expects a neighbor list of shape (K, 2)")
+    _check_aabb(aabbMin, aabbMax, batchSize, "ComputePDFOp")
+    kd = _cnt(neighbors)
+    pdf = ops.compute_pdf(inPts, inBatchIds.reshape(-1), aabbMin, aabbMax, startIndexs.reshape(-1), neighbors, window,
+                          radius, scaleInv, _cnt(startIndexs), kd)
+    return _tag(pdf.reshape(-1, 1), kd)
+
+
+def poisson_sampling(inPts, inBatchIds, cellIndexs, aabbMin, aabbMax, radius, batchSize, scaleInv):
+    """PoissonSampling, tf_ops/poisson_sampling.cc:26-45,109-211 -> (pts [M,3], batchIds [M,1], indexs [M])."""
+    _req(radius > 0.0, "PoissonSamplingOp expects a positive radius")
+    _req(batchSize > 0, "PoissonSamplingOp expects a positive batch size")
+    _req(inPts.dim() == 2 and inPts.shape[1] == 3, "PoissonSamplingOp expects points with three components")
+    _check_bids(inBatchIds, inPts.shape[0], "PoissonSamplingOp")
+    _req(cellIndexs.dim() == 5 and cellIndexs.shape[0] == batchSize,
+         "PoissonSamplingOp expects a five dimension tensor for the cell indices")
+    _check_aabb(aabbMin, aabbMax, batchSize, "PoissonSamplingOp")
+    nd = _cnt(inPts)
+    if _rt.mode() == "planned":
+        plan = _rt.current_plan()
+        p, b, idx, m_dev = ops.poisson_sampling(inPts, inBatchIds.reshape(-1), cellIndexs, aabbMin, aabbMax, radius,
+                                                batchSize, scaleInv, nd, plan.next_capacity(), plan.overflow)
+        return _tag(p, m_dev), _tag(b.reshape(-1, 1), m_dev), _tag(idx, m_dev)
+    p, b, idx, m_dev = ops.poisson_sampling(inPts, inBatchIds.reshape(-1), cellIndexs, aabbMin, aabbMax, radius,
+                                            batchSize, scaleInv, nd)
+    M = int(m_dev.item())  # host sync, as poisson_sampling.cu:222
+    if _rt.mode() == "record":
+        _rt.current_plan().sizes.append(M)
+    return p[:M].clone(), b[:M].clone().reshape(-1, 1), idx[:M].clone()
+
+
+def get_sampled_features(inSampledIndexs, pInFeatures):
+    """GetSampledFeatures, tf_ops/poisson_sampling.cc:47-55,213-250."""
+    _req(inSampledIndexs.dim() == 1, "GetSampledFeaturesOp expects indexs of shape (numSamples)")
+    _req(pInFeatures.dim() == 2, "GetSampledFeaturesOp expects features of shape (numPoints, C)")
+    md = _cnt(inSampledIndexs)
+    return _tag(ops.get_sampled_features(inSampledIndexs, pInFeatures, md), md)
+
+
+def spatial_conv(inPts, inFeatures, inBatchIds, inPDFs, inSamplePts, neighStartIndexs, packedNeighs, aabbMin, aabbMax,
+                 weights1, weights2, weightsOut, biases1, biases2, biasesOut, numOutFeatures, combin, batchSize,
+                 radius, scaleInv, avg):
+    """SpatialConv, tf_ops/spatial_conv.cc:24-54,179-311 -> out [M, numOutFeatures].
+
+    Weight tensors carry the TF shapes ([3, 8nb], [8, 8nb], [8, 8nb]) but are read as the flat buffers the
+    reference kernel indexes (spatial_conv.cu:49-73,172) -- a reinterpretation, not a transpose."""
+    _req(numOutFeatures > 0, "SpatialConvOp expects a positive number of output features")
+    _req(radius > 0.0, "SpatialConvOp expects a positive radius")
+    _req(batchSize > 0, "SpatialConvOp expects a positive batch size")
+    _req(inPts.dim() == 2 and inPts.shape[1] == 3, "SpatialConvOp expects points with three components")
+    N = inPts.shape[0]
+    _req(inFeatures.dim() == 2 and inFeatures.shape[0] == N, "SpatialConvOp expects features of shape (numPoints, C)")
+    C = inFeatures.shape[1]
+    _check_bids(inBatchIds, N, "SpatialConvOp")
+    _req(inPDFs.dim() == 2 and inPDFs.shape[1] == 1, "SpatialConvOp expects pdfs of shape (K, 1)")
+    K = inPDFs.shape[0]
+    _req(inSamplePts.dim() == 2 and inSamplePts.shape[1] == 3, "SpatialConvOp expects samples with three components")
+    M = inSamplePts.shape[0]
+    _req(neighStartIndexs.dim() == 2 and tuple(neighStartIndexs.shape) == (M, 1),
+         "SpatialConvOp expects start indexs of shape (numSamples, 1)")
+    _req(packedNeighs.dim() == 2 and tuple(packedNeighs.shape) == (K, 2),
+         "SpatialConvOp expects a neighbor list of shape (K, 2)")
+    _check_aabb(aabbMin, aabbMax, batchSize, "SpatialConvOp")
+    bs = ops.get_block_size()
+    _req(weights1.dim() == 2 and weights1.shape[0] == 3 and biases1.dim() == 1 and
+         weights1.shape[1] == biases1.shape[0] and weights1.shape[1] % bs == 0,
+         "SpatialConvOp expects a correct first hidden layer")
+    _req(weights2.dim() == 2 and weights2.shape[0] == bs and biases2.dim() == 1 and
+         weights2.shape[1] == biases2.shape[0] and weights2.shape[1] == weights1.shape[1],
+         "SpatialConvOp expects a correct second hidden layer")
+    _req(weightsOut.dim() == 2 and weightsOut.shape[0] == bs and biasesOut.dim() == 1 and
+         weightsOut.shape[1] == biasesOut.shape[0], "SpatialConvOp expects a correct output layer")
+    _req(weightsOut.shape[1] % C == 0,
+         "SpatialConvOp expects a number of output neurons multiple of the number of features.")
+    if not combin:
+        _req(weightsOut.shape[1] == C, "SpatialConvOp expects the same number of features in the input and the output")
+        _req(numOutFeatures == C, "SpatialConvOp expects the same number of features in the input and the output")
+    nOut = C * numOutFeatures if combin else C
+    _req(weights1.shape[1] >= (nOut + bs - 1) // bs * bs, "SpatialConvOp expects enough neurons for the output")
+    md = _cnt(inSamplePts)
+    out = ops.spatial_conv(inPts, inFeatures, inBatchIds.reshape(-1), inPDFs.reshape(-1), inSamplePts,
+                           neighStartIndexs.reshape(-1), packedNeighs, aabbMin, aabbMax, weights1, biases1, weights2,
+                           biases2, weightsOut, biasesOut, numOutFeatures, combin, radius, scaleInv, avg, md,
+                           _cnt(packedNeighs))
+    return _tag(out, md)

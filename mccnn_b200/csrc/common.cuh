@@ -1,0 +1,111 @@
+// common.cuh -- shared device helpers for the sm_100a Monte-Carlo-convolution kernels.
+//
+// The geometry helpers reproduce, operation for operation, the float arithmetic the reference's
+// kernels compile to (tf_ops/sort_gpu.cu:50-59, tf_ops/find_neighbors.cu:67-97): every index-valued
+// result downstream (cell keys, neighbour lists, Poisson samples) depends on these bits.
+#pragma once
+#include <cuda_runtime.h>
+#include <float.h>
+#include <stdint.h>
+
+#define MC_BLOCK_MLP 8  // BLOCK_MLP_SIZE of the reference build (tf_ops/genCompileScript.py:20)
+#define MC_FULL_MASK 0xffffffffu
+
+namespace mc {
+
+// Every dynamic extent is passed as (device pointer, host capacity): kernels are launched over the
+// capacity and read the live count on the device, so no host sync is needed between ops.
+__device__ __forceinline__ int live_count(const int* __restrict__ dCount, int capacity) {
+    if (dCount == nullptr) return capacity;
+    int v = *dCount;
+    return v < capacity ? v : capacity;
+}
+
+__device__ __forceinline__ float max_extent(const float* __restrict__ mn, const float* __restrict__ mx, int b) {
+    float ex = mx[b * 3] - mn[b * 3];
+    float ey = mx[b * 3 + 1] - mn[b * 3 + 1];
+    float ez = mx[b * 3 + 2] - mn[b * 3 + 2];
+    return fmaxf(fmaxf(ex, ey), ez);
+}
+
+// max(min((int)floor(v), n-1), 0); __float2int_rd saturates and maps NaN to 0 like the reference's cast.
+__device__ __forceinline__ int clamp_cell(float v, int n) {
+    int c = __float2int_rd(v);
+    c = c < n - 1 ? c : n - 1;
+    return c > 0 ? c : 0;
+}
+
+struct CloudFrame {  // per-cloud constants every geometric kernel needs
+    float mnx, mny, mnz;
+    float cell;    // extent / n
+    float radius;  // scaled radius
+};
+
+__device__ __forceinline__ CloudFrame cloud_frame(const float* __restrict__ mn, const float* __restrict__ mx,
+                                                  int b, int n, float radius, bool scaleInv) {
+    CloudFrame f;
+    float ext = max_extent(mn, mx, b);
+    f.mnx = mn[b * 3];
+    f.mny = mn[b * 3 + 1];
+    f.mnz = mn[b * 3 + 2];
+    f.cell = __fdiv_rn(ext, (float)n);
+    f.radius = scaleInv ? __fmul_rn(radius, ext) : radius;
+    return f;
+}
+
+__device__ __forceinline__ void cell_of(const CloudFrame& f, float x, float y, float z, int n, int& cx, int& cy,
+                                        int& cz) {
+    cx = clamp_cell(__fdiv_rn(__fsub_rn(x, f.mnx), f.cell), n);
+    cy = clamp_cell(__fdiv_rn(__fsub_rn(y, f.mny), f.cell), n);
+    cz = clamp_cell(__fdiv_rn(__fsub_rn(z, f.mnz), f.cell), n);
+}
+
+// sqrt(dx*dx + dy*dy + dz*dz) < r exactly as the reference's SASS evaluates it:
+// FMUL dy*dy ; FFMA dx*dx+. ; FFMA dz*dz+. ; IEEE sqrt ; FSETP.LT   (see DESIGN.md "float-exact predicates")
+__device__ __forceinline__ bool within_radius(float px, float py, float pz, float qx, float qy, float qz, float r) {
+    float dx = __fsub_rn(qx, px), dy = __fsub_rn(qy, py), dz = __fsub_rn(qz, pz);
+    float d2 = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+    return __fsqrt_rn(d2) < r;
+}
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+__device__ __forceinline__ int warp_inclusive_scan(int v) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int t = __shfl_up_sync(MC_FULL_MASK, v, d);
+        if (lane_id() >= d) v += t;
+    }
+    return v;
+}
+
+// 27-cell neighbourhood tables.  Order is observable behaviour:
+//  kOffsNeigh: tf_ops/find_neighbors.cu:282-291 ; kOffsPool: tf_ops/poisson_sampling.cu:192-196
+__device__ __constant__ const signed char kOffsNeigh[27][3] = {
+    {1, 1, 1},   {0, 1, 1},   {-1, 1, 1},  {1, 0, 1},   {0, 0, 1},   {-1, 0, 1},  {1, -1, 1},
+    {0, -1, 1},  {-1, -1, 1}, {1, 1, 0},   {0, 1, 0},   {-1, 1, 0},  {1, 0, 0},   {0, 0, 0},
+    {-1, 0, 0},  {1, -1, 0},  {0, -1, 0},  {-1, -1, 0}, {1, 1, -1},  {0, 1, -1},  {-1, 1, -1},
+    {1, 0, -1},  {0, 0, -1},  {-1, 0, -1}, {1, -1, -1}, {0, -1, -1}, {-1, -1, -1}};
+
+__device__ __constant__ const signed char kOffsPool[27][3] = {
+    {1, 1, -1},  {0, -1, 1},  {0, 1, 1},  {0, 1, 0}, {0, 0, 1},  {0, -1, 0},  {-1, 1, -1},
+    {0, -1, -1}, {1, 0, 0},   {1, -1, 1}, {1, 0, 1}, {-1, 1, 1}, {-1, 0, 0},  {1, -1, -1},
+    {0, 1, -1},  {-1, -1, 0}, {-1, 1, 0}, {0, 0, 0}, {0, 0, -1}, {1, 1, 0},   {1, 0, -1},
+    {1, -1, 0},  {-1, 0, 1},  {1, 1, 1},  {-1, 0, -1}, {-1, -1, -1}, {-1, -1, 1}};
+
+}  // namespace mc
+
+// ---- host side -------------------------------------------------------------------------------
+namespace mc {
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);  // cudaPeekAtLastError -> status + message
+inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+}  // namespace mc
+
+#define MC_REQUIRE(cond, ...)          \
+    do {                               \
+        if (!(cond)) {                 \
+            mc::set_error(__VA_ARGS__); \
+            return 1;                  \
+        }                              \
+    } while (0)

@@ -1,0 +1,119 @@
+// neighbors.cu -- fixed-radius neighbour lists (CSR: start[M], pairs[K,2] = (point j, sample i)) over the grid.
+//
+// Replaces countNeighbors / computeOffsets / findNeighbors (tf_ops/find_neighbors.cu:40-264).  The reference runs
+// one THREAD per sample (a serial walk over up to 27 cells x population, uncoalesced), a cudaMalloc + symbol
+// upload + blocking D2H for the total, and Hillis-Steele scans.  Here one WARP owns a sample: lanes 0..26 fetch the
+// 27 cell ranges at once, then the warp sweeps the non-empty cells with one candidate per lane (coalesced 12-byte
+// rows), and __ballot_sync/__popc give both the count and the ORDERED write slot, so the output order is exactly
+// the reference's (cells in table order find_neighbors.cu:282-291, ascending j inside a cell).  The predicate is
+// the float-exact one in common.cuh.  The total stays on the device (dNumNeighbors); the caller decides whether to
+// read it (exact-shape API) or to keep going with a capacity-sized pair buffer (sync-free pipeline).
+#include "common.cuh"
+#include "scan.cuh"
+
+namespace mc {
+namespace {
+
+constexpr int kWarpsPerCta = 8;
+
+template <bool FILL>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+    neighbors_kernel(bool scaleInv, const int* __restrict__ dM, int capM, int n, float radius,
+                     const float* __restrict__ samples, const int* __restrict__ sbids,
+                     const float* __restrict__ pts2, const int2* __restrict__ cellIdx, const float* __restrict__ mn,
+                     const float* __restrict__ mx, int* __restrict__ start, const int* __restrict__ tileOffs,
+                     int2* __restrict__ pairs, int capK, int* __restrict__ dOverflow) {
+    const int M = live_count(dM, capM);
+    const int i = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+    if (i >= M) return;
+    const int lane = lane_id();
+    const int b = sbids[i];
+    const CloudFrame f = cloud_frame(mn, mx, b, n, radius, scaleInv);
+    const float sx = samples[(size_t)i * 3], sy = samples[(size_t)i * 3 + 1], sz = samples[(size_t)i * 3 + 2];
+    int cx, cy, cz;
+    cell_of(f, sx, sy, sz, n, cx, cy, cz);
+
+    // lanes 0..26: (lo,hi) of neighbour cell `lane`
+    int lo = 0, hi = 0;
+    if (lane < 27) {
+        int x = cx + kOffsNeigh[lane][0], y = cy + kOffsNeigh[lane][1], z = cz + kOffsNeigh[lane][2];
+        if (x >= 0 && x < n && y >= 0 && y < n && z >= 0 && z < n) {
+            int2 c = cellIdx[(((size_t)b * n + x) * n + y) * n + z];
+            lo = c.x;
+            hi = c.y;
+        }
+    }
+    unsigned nonEmpty = __ballot_sync(MC_FULL_MASK, hi > lo);
+
+    int base = 0;
+    if (FILL) {
+        base = start[i] + tileOffs[i / kScanTile];
+        if (lane == 0) start[i] = base;  // finalise in place, as find_neighbors.cu:223-224
+    }
+    const unsigned ltMask = (1u << lane) - 1u;
+    int count = 0;
+    while (nonEmpty) {
+        int o = __ffs(nonEmpty) - 1;
+        nonEmpty &= nonEmpty - 1;
+        const int clo = __shfl_sync(MC_FULL_MASK, lo, o), chi = __shfl_sync(MC_FULL_MASK, hi, o);
+        for (int j0 = clo; j0 < chi; j0 += 32) {
+            int j = j0 + lane;
+            bool in = false;
+            if (j < chi)
+                in = within_radius(sx, sy, sz, pts2[(size_t)j * 3], pts2[(size_t)j * 3 + 1], pts2[(size_t)j * 3 + 2],
+                                   f.radius);
+            unsigned hit = __ballot_sync(MC_FULL_MASK, in);
+            if (FILL && in) {
+                int slot = base + count + __popc(hit & ltMask);
+                if (slot < capK)
+                    pairs[slot] = make_int2(j, i);
+                else if (dOverflow != nullptr)
+                    *dOverflow = 1;
+            }
+            count += __popc(hit);
+        }
+    }
+    if (!FILL && lane == 0) start[i] = count;
+}
+
+}  // namespace
+}  // namespace mc
+
+using namespace mc;
+
+extern "C" long long mc_find_neighbors_workspace_ints(int numSamples) { return scan_num_tiles(numSamples) + 8; }
+
+// countNeighborsCPU, tf_ops/find_neighbors.cu:268-317 -- without the cudaMalloc / D2H: the total lands in
+// *dNumNeighbors (device).  startIdx receives the tile-local exclusive prefix; mc_find_neighbors_pack finalises it.
+extern "C" int mc_find_neighbors_count(int scaleInv, int numSamples, const int* dNumSamples, int numCells,
+                                       float radius, const float* samples, const int* sampleBatchIds,
+                                       const float* pts2, const int* cellIdx, const float* aabbMin,
+                                       const float* aabbMax, int* startIdx, int* workspace, int* dNumNeighbors,
+                                       void* stream) {
+    MC_REQUIRE(radius > 0.0f, "mc_find_neighbors: radius must be positive");
+    MC_REQUIRE(numCells > 0, "mc_find_neighbors: cell count must be positive");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (numSamples > 0)
+        neighbors_kernel<false><<<cdiv(numSamples, kWarpsPerCta), kWarpsPerCta * 32, 0, s>>>(
+            scaleInv != 0, dNumSamples, numSamples, numCells, radius, samples, sampleBatchIds, pts2,
+            reinterpret_cast<const int2*>(cellIdx), aabbMin, aabbMax, startIdx, nullptr, nullptr, 0, nullptr);
+    launch_scan(startIdx, dNumSamples, numSamples, workspace, dNumNeighbors, s);
+    return check_launch("mc_find_neighbors_count");
+}
+
+// packNeighborsCPU, tf_ops/find_neighbors.cu:330-371.  pairs holds capacityPairs (j,i) rows; rows past the
+// capacity are dropped and *dOverflow is set (caller zeroes it beforehand).
+extern "C" int mc_find_neighbors_pack(int scaleInv, int numSamples, const int* dNumSamples, int numCells,
+                                      float radius, const float* samples, const int* sampleBatchIds,
+                                      const float* pts2, const int* cellIdx, const float* aabbMin,
+                                      const float* aabbMax, int* startIdx, const int* workspace, int* pairs,
+                                      int capacityPairs, int* dOverflow, void* stream) {
+    MC_REQUIRE(radius > 0.0f, "mc_find_neighbors: radius must be positive");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (numSamples > 0)
+        neighbors_kernel<true><<<cdiv(numSamples, kWarpsPerCta), kWarpsPerCta * 32, 0, s>>>(
+            scaleInv != 0, dNumSamples, numSamples, numCells, radius, samples, sampleBatchIds, pts2,
+            reinterpret_cast<const int2*>(cellIdx), aabbMin, aabbMax, startIdx, workspace,
+            reinterpret_cast<int2*>(pairs), capacityPairs, dOverflow);
+    return check_launch("mc_find_neighbors_pack");
+}

@@ -1,0 +1,205 @@
+"""Raw, sync-free bindings of the C-ABI on torch CUDA tensors.
+
+Each function enqueues kernels on torch's current CUDA stream and returns immediately.  Dynamic extents follow the
+C-ABI convention: a tensor is allocated with a *capacity* number of rows and an optional int32[1] device tensor
+(`n_dev`, `m_dev`, `k_dev`) holds the live row count.  `MCConvModule` (the reference's op API) wraps these with
+exact output shapes; `MCConvBuilder`'s planned mode keeps the capacities and never blocks the host.
+
+torch is used for device memory and streams only -- no arithmetic of the hot path happens in torch.
+"""
+import ctypes
+
+import torch
+
+from ._lib import lib, check
+
+_i32 = torch.int32
+_f32 = torch.float32
+
+
+def _p(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _dev(t):
+    if not t.is_cuda:
+        raise RuntimeError("mccnn_b200: tensors must live on a CUDA device (there is no CPU path)")
+    return t.device
+
+
+def _f(t):
+    if t.dtype != _f32:
+        raise ValueError("expected a float32 tensor, got %s" % t.dtype)
+    return t.contiguous()
+
+
+def _i(t):
+    if t.dtype != _i32:
+        raise ValueError("expected an int32 tensor, got %s" % t.dtype)
+    return t.contiguous()
+
+
+def new_count(device, value=0):
+    return torch.full((1,), value, dtype=_i32, device=device)
+
+
+def get_block_size():
+    return int(lib.mc_get_block_size())
+
+
+def compute_aabb(pts, bids, batch_size, scale_inv):
+    pts, bids = _f(pts), _i(bids)
+    dev = _dev(pts)
+    mn = torch.empty((batch_size, 3), dtype=_f32, device=dev)
+    mx = torch.empty((batch_size, 3), dtype=_f32, device=dev)
+    ws = torch.empty((1,), dtype=_i32, device=dev)
+    check(lib.mc_compute_aabb(int(scale_inv), pts.shape[0], batch_size, _p(pts), _p(bids), _p(mn), _p(mx), _p(ws),
+                              _stream()))
+    return mn, mx
+
+
+def num_cells(cell_size, scale_inv, aabb_min, aabb_max):
+    """determineNumCells; blocks the host only when scale_inv is False (needs row 0 of the box)."""
+    out = ctypes.c_int(0)
+    ws = None if scale_inv else torch.empty((1,), dtype=_i32, device=aabb_min.device)
+    check(lib.mc_determine_num_cells(int(scale_inv), float(cell_size), _p(aabb_min), _p(aabb_max), _p(ws),
+                                     ctypes.byref(out), _stream()))
+    return out.value
+
+
+def sort_points_step1(pts, bids, aabb_min, aabb_max, batch_size, n_cells, n_dev=None):
+    pts, bids = _f(pts), _i(bids)
+    dev = _dev(pts)
+    N = pts.shape[0]
+    keys = torch.empty((N,), dtype=_i32, device=dev)
+    new_idx = torch.empty((N,), dtype=_i32, device=dev)
+    ws = torch.empty((lib.mc_sort_step1_workspace_ints(N, batch_size, n_cells),), dtype=_i32, device=dev)
+    check(lib.mc_sort_points_step1(N, _p(n_dev), batch_size, n_cells, _p(aabb_min), _p(aabb_max), _p(pts), _p(bids),
+                                   _p(ws), _p(keys), _p(new_idx), _stream()))
+    return keys, new_idx
+
+
+def sort_points_step2(pts, bids, feats, keys, new_idx, batch_size, n_cells, n_dev=None):
+    pts, bids, feats, keys, new_idx = _f(pts), _i(bids), _f(feats), _i(keys), _i(new_idx)
+    dev = _dev(pts)
+    N, C = pts.shape[0], feats.shape[1]
+    out_pts = torch.empty_like(pts)
+    out_bids = torch.empty_like(bids)
+    out_feats = torch.empty_like(feats)
+    cell_idx = torch.empty((batch_size, n_cells, n_cells, n_cells, 2), dtype=_i32, device=dev)
+    ws = torch.empty((max(N, 1),), dtype=_i32, device=dev)
+    check(lib.mc_sort_points_step2(N, _p(n_dev), batch_size, C, n_cells, _p(pts), _p(bids), _p(feats), _p(keys),
+                                   _p(new_idx), _p(ws), _p(out_pts), _p(out_bids), _p(out_feats), _p(cell_idx),
+                                   _stream()))
+    return out_pts, out_bids, out_feats, cell_idx
+
+
+def sort_features(feats, new_idx, n_dev=None):
+    feats, new_idx = _f(feats), _i(new_idx)
+    out = torch.empty_like(feats)
+    check(lib.mc_sort_features(feats.shape[0], _p(n_dev), feats.shape[1], _p(feats), _p(new_idx), _p(out),
+                               _stream()))
+    return out
+
+
+def sort_features_back(feats, new_idx, n_dev=None):
+    feats, new_idx = _f(feats), _i(new_idx)
+    out = torch.empty_like(feats)
+    check(lib.mc_sort_features_back(feats.shape[0], _p(n_dev), feats.shape[1], _p(feats), _p(new_idx), _p(out),
+                                    _stream()))
+    return out
+
+
+def transform_indexs(idx, new_idx, m_dev=None, n_dev=None):
+    idx, new_idx = _i(idx), _i(new_idx)
+    dev = _dev(idx)
+    out = torch.empty_like(idx)
+    ws = torch.empty((max(new_idx.shape[0], 1),), dtype=_i32, device=dev)
+    check(lib.mc_transform_indexs(idx.shape[0], _p(m_dev), new_idx.shape[0], _p(n_dev), _p(idx), _p(new_idx), _p(ws),
+                                  _p(out), _stream()))
+    return out
+
+
+def find_neighbors_count(samples, sbids, pts2, cell_idx, aabb_min, aabb_max, radius, scale_inv, m_dev=None):
+    """First phase: per-sample counts scanned in place; returns (start_local, workspace, k_dev)."""
+    samples, sbids, pts2, cell_idx = _f(samples), _i(sbids), _f(pts2), _i(cell_idx)
+    dev = _dev(samples)
+    M = samples.shape[0]
+    start = torch.empty((M,), dtype=_i32, device=dev)
+    ws = torch.empty((lib.mc_find_neighbors_workspace_ints(M),), dtype=_i32, device=dev)
+    k_dev = torch.empty((1,), dtype=_i32, device=dev)
+    check(lib.mc_find_neighbors_count(int(scale_inv), M, _p(m_dev), cell_idx.shape[1], float(radius), _p(samples),
+                                      _p(sbids), _p(pts2), _p(cell_idx), _p(aabb_min), _p(aabb_max), _p(start),
+                                      _p(ws), _p(k_dev), _stream()))
+    return start, ws, k_dev
+
+
+def find_neighbors_pack(samples, sbids, pts2, cell_idx, aabb_min, aabb_max, radius, scale_inv, start, ws, capacity,
+                        m_dev=None, overflow=None):
+    """Second phase: finalises `start` in place and fills pairs[capacity, 2]."""
+    samples, sbids, pts2, cell_idx = _f(samples), _i(sbids), _f(pts2), _i(cell_idx)
+    dev = _dev(samples)
+    pairs = torch.empty((capacity, 2), dtype=_i32, device=dev)
+    check(lib.mc_find_neighbors_pack(int(scale_inv), samples.shape[0], _p(m_dev), cell_idx.shape[1], float(radius),
+                                     _p(samples), _p(sbids), _p(pts2), _p(cell_idx), _p(aabb_min), _p(aabb_max),
+                                     _p(start), _p(ws), _p(pairs), capacity, _p(overflow), _stream()))
+    return pairs
+
+
+def compute_pdf(pts, bids, aabb_min, aabb_max, start, pairs, window, radius, scale_inv, m_dev=None, k_dev=None):
+    pts, bids, start, pairs = _f(pts), _i(bids), _i(start), _i(pairs)
+    dev = _dev(pts)
+    K = pairs.shape[0]
+    pdf = torch.empty((K,), dtype=_f32, device=dev)
+    check(lib.mc_compute_pdf(int(scale_inv), float(window), start.shape[0], _p(m_dev), K, _p(k_dev), float(radius),
+                             _p(pts), _p(bids), _p(aabb_min), _p(aabb_max), _p(start), _p(pairs), _p(pdf),
+                             _stream()))
+    return pdf
+
+
+def poisson_sampling(pts, bids, cell_idx, aabb_min, aabb_max, radius, batch_size, scale_inv, n_dev=None,
+                     capacity=None, overflow=None):
+    """Returns (out_pts[cap,3], out_bids[cap], out_idx[cap], m_dev)."""
+    pts, bids, cell_idx = _f(pts), _i(bids), _i(cell_idx)
+    dev = _dev(pts)
+    N = pts.shape[0]
+    cap = N if capacity is None else min(capacity, N)
+    out_pts = torch.empty((cap, 3), dtype=_f32, device=dev)
+    out_bids = torch.empty((cap,), dtype=_i32, device=dev)
+    out_idx = torch.empty((cap,), dtype=_i32, device=dev)
+    m_dev = torch.empty((1,), dtype=_i32, device=dev)
+    ws = torch.empty((lib.mc_poisson_workspace_ints(N, batch_size),), dtype=_i32, device=dev)
+    check(lib.mc_poisson_sampling(int(scale_inv), float(radius), N, _p(n_dev), batch_size, cell_idx.shape[1],
+                                  _p(aabb_min), _p(aabb_max), _p(pts), _p(bids), _p(cell_idx), _p(ws), cap,
+                                  _p(out_pts), _p(out_bids), _p(out_idx), _p(m_dev), _p(overflow), _stream()))
+    return out_pts, out_bids, out_idx, m_dev
+
+
+def get_sampled_features(idx, feats, m_dev=None):
+    idx, feats = _i(idx), _f(feats)
+    out = torch.empty((idx.shape[0], feats.shape[1]), dtype=_f32, device=_dev(feats))
+    check(lib.mc_get_sampled_features(idx.shape[0], _p(m_dev), feats.shape[1], _p(idx), _p(feats), _p(out),
+                                      _stream()))
+    return out
+
+
+def spatial_conv(pts, feats, bids, pdfs, samples, start, pairs, aabb_min, aabb_max, w1, b1, w2, b2, wout, bout,
+                 num_out_features, combin, radius, scale_inv, avg, m_dev=None, k_dev=None):
+    """Parameters in the OP's order (W1, b1, W2, b2, Wout, bout), flat reference layouts."""
+    pts, feats, bids, pdfs, samples = _f(pts), _f(feats), _i(bids), _f(pdfs), _f(samples)
+    start, pairs = _i(start), _i(pairs)
+    w1, b1, w2, b2, wout, bout = (_f(t) for t in (w1, b1, w2, b2, wout, bout))
+    dev = _dev(pts)
+    M, K, C = samples.shape[0], pairs.shape[0], feats.shape[1]
+    out = torch.empty((M, num_out_features), dtype=_f32, device=dev)
+    ws_n = lib.mc_spatial_conv_workspace_floats(M, C, num_out_features, int(combin))
+    ws = torch.empty((ws_n,), dtype=_f32, device=dev) if ws_n > 0 else None
+    check(lib.mc_spatial_conv(int(avg), int(scale_inv), K, _p(k_dev), C, num_out_features, M, _p(m_dev), int(combin),
+                              float(radius), _p(pts), _p(bids), _p(feats), _p(pdfs), _p(samples), _p(start),
+                              _p(pairs), _p(aabb_min), _p(aabb_max), _p(w1), _p(b1), _p(w2), _p(b2), _p(wout),
+                              _p(bout), _p(ws), _p(out), _stream()))
+    return out

@@ -1,0 +1,75 @@
+"""Seeded synthetic inputs shared by the parity tests, golden-vector script, smoke() and bench.py
+(uniform-in-cube and sphere-surface clouds, Glorot weights, biases U(-0.1, 0.1))."""
+import math
+
+import numpy as np
+
+
+def make_cloud(n, dist, rng):
+    if dist == "cube":
+        return rng.uniform(-0.5, 0.5, (n, 3)).astype(np.float32)
+    if dist == "sphere":  # ModelNet-like: points on a surface
+        v = rng.normal(size=(n, 3))
+        v /= np.linalg.norm(v, axis=1, keepdims=True)
+        return (0.5 * v).astype(np.float32)
+    if dist == "room":  # ScanNet-like: faces of a 6 x 4 x 2.5 m box, density thinned along x (utils/DataSet.py:464-466)
+        L = np.array([6.0, 4.0, 2.5])
+        out = []
+        while sum(len(o) for o in out) < n:
+            m = 4 * n
+            face = rng.integers(0, 6, m)
+            p = rng.uniform(-0.5, 0.5, (m, 3)) * L
+            ax = face // 2
+            p[np.arange(m), ax] = np.where(face % 2 == 0, -0.5, 0.5) * L[ax]
+            keep = rng.uniform(size=m) < np.sqrt(np.clip((p[:, 0] / L[0] + 0.5 - 0.2) / 0.6, 0.01, 1.0))
+            out.append(p[keep])
+        return np.concatenate(out)[:n].astype(np.float32)
+    raise ValueError(dist)
+
+
+def make_batch(batch, n, dist="sphere", seed=0, num_features=1, ragged=False):
+    """Packed batch: points [sum N, 3], batch ids int32 [sum N, 1] (cloud-contiguous, utils/DataSet.py:816-818),
+    features [sum N, C] (ones when C == 1, as utils/DataSet.py:822, else U(-1, 1))."""
+    pts, bids = [], []
+    for b in range(batch):
+        rng = np.random.default_rng(seed * 1000 + b)
+        nb = n if not ragged else max(1, int(n * rng.uniform(0.3, 1.0)))
+        pts.append(make_cloud(nb, dist, rng))
+        bids.append(np.full((nb, 1), b, np.int32))
+    pts = np.concatenate(pts)
+    bids = np.concatenate(bids)
+    rng = np.random.default_rng(seed + 77)
+    if num_features == 1:
+        feats = np.ones((pts.shape[0], 1), np.float32)
+    else:
+        feats = rng.uniform(-1, 1, (pts.shape[0], num_features)).astype(np.float32)
+    return pts, bids, feats
+
+
+def make_conv_weights(num_in, num_out, combin, seed=0, block=8):
+    """TF-shaped parameter tensors of one convolution (utils/MCConvBuilder.py:397-419), python-API order."""
+    rng = np.random.default_rng(seed + 1234)
+    n_out = num_in * num_out if combin else num_in
+    nb = (n_out + block - 1) // block
+
+    def glorot(shape, fi, fo):
+        lim = math.sqrt(3.0 / ((fi + fo) / 2.0))
+        return rng.uniform(-lim, lim, shape).astype(np.float32)
+
+    w1 = glorot((3, block * nb), 3, block * nb)
+    w2 = glorot((nb, block, block), block * nb, block * nb).reshape(block, nb * block)
+    w3 = glorot((nb, block, block), block * nb, block * nb).reshape(block, nb * block)
+    b1 = rng.uniform(-0.1, 0.1, (block * nb,)).astype(np.float32)
+    b2 = rng.uniform(-0.1, 0.1, (block * nb,)).astype(np.float32)
+    b3 = rng.uniform(-0.1, 0.1, (block * nb,)).astype(np.float32)
+    return w1, w2, w3, b1, b2, b3
+
+
+def rel_err(a, b, atol_scale=1e-6):
+    """max |a-b| / (max(|a|,|b|) + atol), atol = atol_scale * max|b| (guards exact cancellations)."""
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    if a.size == 0:
+        return 0.0
+    atol = atol_scale * (np.abs(b).max() if b.size else 1.0)
+    return float((np.abs(a - b) / (np.maximum(np.abs(a), np.abs(b)) + atol)).max())

@@ -1,0 +1,105 @@
+"""MCClassS forward (models/MCClassS.py topology) through the builder API on the GPU:
+  * exact mode vs the same network assembled from the CPU oracle ops (indices bit-exact, logits to tolerance);
+  * planned (sync-free) and CUDA-graph replays reproduce the exact-mode logits BIT FOR BIT (all kernels deterministic);
+  * capacity overflow is detected and repaired, never silently truncated.
+"""
+import numpy as np
+import pytest
+
+from common import make_batch
+
+pytestmark = pytest.mark.gpu
+
+
+def _randomize_store(store, seed=0):
+    """non-trivial biases / batch-norm statistics so that every parameter path is exercised"""
+    import torch
+    g = torch.Generator(device="cpu")
+    g.manual_seed(seed)
+    for name, v in store.vars.items():
+        if name.endswith("moving_variance"):
+            v.copy_((torch.rand(v.shape, generator=g) * 0.5 + 0.75).to(v.device))
+        elif "biases" in name or name.endswith("beta") or name.endswith("moving_mean"):
+            v.copy_(((torch.rand(v.shape, generator=g) - 0.5) * 0.2).to(v.device))
+        elif name.endswith("gamma"):
+            v.copy_((torch.rand(v.shape, generator=g) * 0.5 + 0.75).to(v.device))
+
+
+def _make(B, k, numCat, dev):
+    import torch
+    from mccnn_b200 import variables
+    from mccnn_b200.models import MCClassS
+    store = variables.VariableStore(device=dev, seed=3)
+
+    def fn(p, b, f):
+        return MCClassS.create_network(p, b, f, 1, B, k, numCat, False, 1.0, 1.0, store=store)
+    return fn, store
+
+
+@pytest.mark.parametrize("B,N,k", [(4, 1024, 16), (32, 1024, 64)])
+def test_mcclasss_exact_planned_graph_identical(B, N, k):
+    import torch
+    from mccnn_b200.engine import PlannedForward
+    dev = torch.device("cuda:0")
+    fn, store = _make(B, k, 40, dev)
+    pts, bids, feats = make_batch(B, N, "sphere", seed=11)
+    tp, tb, tf = (torch.from_numpy(a).to(dev) for a in (pts, bids, feats))
+    ref = fn(tp, tb, tf)                      # creates the variables
+    _randomize_store(store)
+    ref = fn(tp, tb, tf)[:B].clone()          # exact mode
+    assert ref.shape == (B, 40) and torch.isfinite(ref).all()
+
+    eng_plain = PlannedForward(fn, B, use_graph=False)
+    eng_graph = PlannedForward(fn, B, use_graph=True)
+    for eng in (eng_plain, eng_graph):
+        first = eng(tp, tb, tf).clone()       # records
+        assert torch.equal(first, ref)
+        for _ in range(3):
+            out = eng(tp, tb, tf).clone()     # planned / replayed
+            assert torch.equal(out, ref)
+    assert eng_graph.stats["captures"] == 1 and eng_graph.stats["replays"] == 3
+
+    # a different batch of the same shape through the same captured graph
+    pts2, bids2, feats2 = make_batch(B, N, "sphere", seed=12)
+    tp2, tb2, tf2 = (torch.from_numpy(a).to(dev) for a in (pts2, bids2, feats2))
+    ref2 = fn(tp2, tb2, tf2)[:B].clone()
+    out2 = eng_graph(tp2, tb2, tf2).clone()
+    assert torch.equal(out2, ref2)
+
+
+def test_capacity_overflow_is_detected_and_repaired():
+    import torch
+    from mccnn_b200.engine import PlannedForward
+    dev = torch.device("cuda:0")
+    B, N, k = 4, 1024, 16
+    fn, store = _make(B, k, 40, dev)
+    sparse = make_batch(B, N, "sphere", seed=21)
+    # same shapes, but every cloud collapsed into a tiny ball around a few far-apart centres: far more neighbours
+    dense_pts = sparse[0].copy()
+    dense_pts[:] = dense_pts * 0.02 + np.sign(dense_pts) * 0.4
+    eng = PlannedForward(fn, B, use_graph=True, slack=1.0)
+    ts = [torch.from_numpy(a).to(dev) for a in sparse]
+    eng(*ts)
+    eng(*ts)
+    td = [torch.from_numpy(dense_pts).to(dev), ts[1], ts[2]]
+    want = fn(*td)[:B].clone()
+    got = eng(*td).clone()
+    assert torch.equal(got, want)
+
+
+def test_mcclasss_matches_oracle_pipeline():
+    import torch
+    from oracle import pipeline as OP
+    dev = torch.device("cuda:0")
+    B, N, k = 4, 1024, 16
+    fn, store = _make(B, k, 40, dev)
+    pts, bids, feats = make_batch(B, N, "sphere", seed=31)
+    tp, tb, tf = (torch.from_numpy(a).to(dev) for a in (pts, bids, feats))
+    fn(tp, tb, tf)
+    _randomize_store(store)
+    got = fn(tp, tb, tf)[:B].cpu().numpy()
+    params = {n: v.cpu().numpy() for n, v in store.vars.items()}
+    want, trace = OP.mcclasss_forward(pts, bids, feats, 1, B, k, 40, params)
+    assert got.shape == want.shape
+    denom = np.abs(want).max()
+    assert np.abs(got - want).max() <= 2e-4 * denom, np.abs(got - want).max() / denom

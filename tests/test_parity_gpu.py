@@ -1,0 +1,229 @@
+"""GPU parity: every op of libmccnn_b200.so, called through the reference-facing Python API (MCConvModule ->
+ctypes -> C ABI), against (a) the CPU oracle (oracle/mccnn_oracle.c) and (b) the reference's own CUDA kernels
+(oracle/_ref/libmccnn_ref.so) on identical seeded inputs.
+
+Bars (BASELINE.json north_star): bit-exact for aabb / sort / find_neighbors / poisson_sampling indices; 1e-5 relative
+for compute_pdf / spatial_conv (float32; the reference's own result is accumulation-order dependent).
+Where the reference is order-nondeterministic (within-cell sort order, poisson output order inside a (cloud, phase)
+launch) the comparison is on the canonicalised form -- see oracle/mccnn_oracle.c header.
+"""
+import numpy as np
+import pytest
+
+from common import make_batch, make_conv_weights, rel_err
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5  # north_star tolerance for compute_pdf / spatial_conv
+
+
+@pytest.fixture(scope="module")
+def env():
+    import torch
+    import mccnn_b200.MCConvModule as M
+    from oracle import cpu as O
+    from oracle import ref as R
+    dev = torch.device("cuda:0")
+
+    def T(a):
+        return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+    def A(t):
+        return t.detach().cpu().numpy()
+
+    return dict(torch=torch, M=M, O=O, R=R if R.available() else None, T=T, A=A, dev=dev)
+
+
+CASES = [
+    # (batch, points per cloud, distribution, ragged, grid radius, scale_inv)
+    (1, 1024, "cube", False, 0.1, True),
+    (1, 1024, "sphere", False, 0.1, True),
+    (4, 1024, "sphere", True, 0.2, True),
+    (32, 1024, "sphere", False, 0.1, True),
+    (3, 700, "cube", True, 0.4, True),
+    (2, 333, "sphere", False, 1.9, True),     # n = 1: whole cloud in one cell
+    (2, 5000, "room", False, 0.25, False),    # absolute radius, batch-global box (ScanNet style)
+]
+
+
+def _grid(e, pts, bids, feats, B, radius, scaleInv, impl):
+    mn, mx = impl.compute_aabb(pts, bids, B, scaleInv)
+    keys, idx = impl.sort_points_step1(pts, bids, mn, mx, B, radius, scaleInv)
+    sp, sb, sf, cells = impl.sort_points_step2(pts, bids, feats, keys, idx, mn, mx, B, radius, scaleInv)
+    return mn, mx, keys, idx, sp, sb, sf, cells
+
+
+@pytest.mark.parametrize("B,N,dist,ragged,radius,scaleInv", CASES)
+def test_aabb_sort_bit_exact(env, B, N, dist, ragged, radius, scaleInv):
+    e = env
+    pts, bids, feats = make_batch(B, N, dist, seed=1, num_features=3, ragged=ragged)
+    o = _grid(e, pts, bids, feats, B, radius, scaleInv, e["O"])
+    g = _grid(e, e["T"](pts), e["T"](bids), e["T"](feats), B, radius, scaleInv, e["M"])
+    names = ["aabbMin", "aabbMax", "keys", "indexs", "sortPts", "sortBatchIds", "sortFeatures", "cellIndexs"]
+    for name, a, b in zip(names, g, o):
+        assert np.array_equal(e["A"](a).reshape(-1), np.asarray(b).reshape(-1)), name
+    if e["R"] is not None and pts.shape[0] % 256 == 0:  # reference aabb has a last-block smem bug otherwise
+        R, T, A = e["R"], e["T"], e["A"]
+        tb = T(bids)
+        rmn, rmx = R.compute_aabb(T(pts), tb, B, scaleInv)
+        assert np.array_equal(A(rmn), A(g[0])) and np.array_equal(A(rmx), A(g[1]))
+    if e["R"] is not None:
+        R, T, A = e["R"], e["T"], e["A"]
+        rkeys, ridx = R.sort_points_step1(T(pts), T(bids), g[0], g[1], B, radius, scaleInv)
+        assert np.array_equal(A(rkeys), A(g[2]))
+        ridx = A(ridx)
+        assert np.array_equal(np.sort(ridx), np.arange(pts.shape[0]))          # a permutation ...
+        skeys = np.empty_like(A(rkeys))
+        skeys[ridx] = A(rkeys)
+        assert np.all(np.diff(skeys) >= 0)                                      # ... that sorts by key
+        rp, rb, rf, rcells = R.sort_points_step2(T(pts), T(bids), T(feats), rkeys, T(ridx.astype(np.int32)), g[0],
+                                                 g[1], B, radius, scaleInv)
+        assert np.array_equal(A(rcells), A(g[7]))                               # cell table is order independent
+
+
+@pytest.mark.parametrize("B,N,dist,ragged,radius,scaleInv", CASES)
+def test_find_neighbors_bit_exact(env, B, N, dist, ragged, radius, scaleInv):
+    e = env
+    O, M, T, A = e["O"], e["M"], e["T"], e["A"]
+    pts, bids, feats = make_batch(B, N, dist, seed=2, num_features=1, ragged=ragged)
+    mn, mx, keys, idx, sp, sb, sf, cells = _grid(e, pts, bids, feats, B, radius, scaleInv, O)
+    # samples = a Poisson sub-sampling (different set than the points) and the points themselves
+    smp, smpb, _ = O.poisson_sampling(sp, sb, cells, mn, mx, radius * 0.5, B, scaleInv)
+    for samples, sbids in ((smp, smpb), (sp, sb)):
+        ostart, opairs = O.find_neighbors(samples, sbids, sp, cells, mn, mx, radius, B, scaleInv)
+        gstart, gpairs = M.find_neighbors(T(samples), T(sbids), T(sp), T(cells), T(mn), T(mx), radius, B, scaleInv)
+        assert np.array_equal(A(gstart), ostart)
+        assert np.array_equal(A(gpairs), opairs)
+        if e["R"] is not None:
+            rstart, rpairs = e["R"].find_neighbors(T(samples), T(sbids), T(sp), T(cells), T(mn), T(mx), radius, B,
+                                                   scaleInv)
+            assert np.array_equal(A(rstart), A(gstart))
+            assert np.array_equal(A(rpairs), A(gpairs))
+
+
+@pytest.mark.parametrize("B,N,dist,ragged,radius,scaleInv", CASES)
+def test_poisson_bit_exact(env, B, N, dist, ragged, radius, scaleInv):
+    e = env
+    O, M, T, A = e["O"], e["M"], e["T"], e["A"]
+    pts, bids, feats = make_batch(B, N, dist, seed=3, num_features=2, ragged=ragged)
+    mn, mx, keys, idx, sp, sb, sf, cells = _grid(e, pts, bids, feats, B, radius, scaleInv, O)
+    op, ob, oi, oph = O.poisson_sampling(sp, sb, cells, mn, mx, radius, B, scaleInv, return_phase=True)
+    gp, gb, gi = M.poisson_sampling(T(sp), T(sb), T(cells), T(mn), T(mx), radius, B, scaleInv)
+    assert np.array_equal(A(gi), oi)
+    assert np.array_equal(A(gb), ob)
+    assert np.array_equal(A(gp), op)
+    # gathers that follow in the hierarchy
+    gf = M.get_sampled_features(gi, T(sf))
+    assert np.array_equal(A(gf), O.get_sampled_features(oi, sf))
+    gt = M.transform_indexs(gi, T(idx))
+    assert np.array_equal(A(gt), O.transform_indexs(oi, idx))
+    if e["R"] is not None:
+        rp, rb, ri = e["R"].poisson_sampling(T(sp), T(sb), T(cells), T(mn), T(mx), radius, B, scaleInv)
+        ri, rb = A(ri), A(rb).reshape(-1)
+        assert ri.shape == oi.shape
+        assert np.array_equal(np.sort(ri), np.sort(oi))               # identical accepted set
+        # the reference emits (cloud, phase) groups in order; inside a group the order is arrival order
+        phase_of = dict(zip(oi.tolist(), oph.tolist()))
+        group = np.array([rb[k] * 27 + phase_of[int(ri[k])] for k in range(ri.shape[0])])
+        assert np.all(np.diff(group) >= 0)
+        assert np.array_equal(A(rp), sp[ri])
+
+
+PDF_CASES = [(1, 1024, "cube", 0.1, 0.2, True), (1, 1024, "sphere", 0.1, 0.2, True),
+             (8, 1024, "sphere", 0.2, 0.2, True), (4, 600, "sphere", 0.8, 0.25, True),
+             (2, 4000, "room", 0.3, 0.25, False)]
+
+
+@pytest.mark.parametrize("B,N,dist,radius,window,scaleInv", PDF_CASES)
+def test_compute_pdf(env, B, N, dist, radius, window, scaleInv):
+    e = env
+    O, M, T, A = e["O"], e["M"], e["T"], e["A"]
+    pts, bids, feats = make_batch(B, N, dist, seed=4)
+    mn, mx, keys, idx, sp, sb, sf, cells = _grid(e, pts, bids, feats, B, radius, scaleInv, O)
+    smp, smpb, _ = O.poisson_sampling(sp, sb, cells, mn, mx, radius * 0.5, B, scaleInv)
+    start, pairs = O.find_neighbors(smp, smpb, sp, cells, mn, mx, radius, B, scaleInv)
+    opdf = O.compute_pdf(sp, sb, mn, mx, start, pairs, window, radius, B, scaleInv)
+    gpdf = M.compute_pdf(T(sp), T(sb), T(mn), T(mx), T(start), T(pairs), window, radius, B, scaleInv)
+    assert gpdf.shape == (pairs.shape[0], 1)
+    err = rel_err(A(gpdf), opdf, atol_scale=0.0)
+    assert err <= RTOL, err
+    if e["R"] is not None:
+        rpdf = e["R"].compute_pdf(T(sp), T(sb), T(mn), T(mx), T(start), T(pairs), window, radius, B, scaleInv)
+        err = rel_err(A(gpdf), A(rpdf), atol_scale=0.0)
+        assert err <= RTOL, err
+
+
+CONV_CASES = [
+    # B, N, dist, C, Co, combin, radius, avg, scaleInv
+    (1, 1024, "cube", 3, 8, True, 0.1, True, True),      # BASELINE config 1
+    (1, 1024, "sphere", 3, 8, True, 0.1, True, True),
+    (4, 1024, "sphere", 1, 64, True, 0.2, True, True),    # MCClassS Conv_1
+    (4, 400, "sphere", 128, 128, False, 0.8, True, True),  # MCClassS Conv_2 shape (depth-wise)
+    (2, 300, "cube", 16, 16, False, 0.5, False, True),     # avg = False
+    (2, 500, "cube", 4, 5, True, 0.3, True, True),         # neurons not a multiple of 8, outputs span blocks
+    (2, 3000, "room", 4, 32, True, 0.3, True, False),      # absolute radius
+]
+
+
+@pytest.mark.parametrize("B,N,dist,C,Co,combin,radius,avg,scaleInv", CONV_CASES)
+def test_spatial_conv(env, B, N, dist, C, Co, combin, radius, avg, scaleInv):
+    e = env
+    O, M, T, A = e["O"], e["M"], e["T"], e["A"]
+    pts, bids, feats = make_batch(B, N, dist, seed=5, num_features=C)
+    if C == 1:
+        feats = np.random.default_rng(9).uniform(-1, 1, feats.shape).astype(np.float32)
+    mn, mx, keys, idx, sp, sb, sf, cells = _grid(e, pts, bids, feats, B, radius, scaleInv, O)
+    smp, smpb, _ = O.poisson_sampling(sp, sb, cells, mn, mx, radius * 0.5, B, scaleInv)
+    start, pairs = O.find_neighbors(smp, smpb, sp, cells, mn, mx, radius, B, scaleInv)
+    pdf = O.compute_pdf(sp, sb, mn, mx, start, pairs, 0.2, radius, B, scaleInv)
+    w1, w2, w3, b1, b2, b3 = make_conv_weights(C, Co, combin, seed=6)
+    oout = O.spatial_conv(sp, sf, sb, pdf, smp, start, pairs, mn, mx, w1, w2, w3, b1, b2, b3, Co, combin, B, radius,
+                          scaleInv, avg, accum_double=True)
+    gout = M.spatial_conv(T(sp), T(sf), T(sb), T(pdf), T(smp), T(start), T(pairs), T(mn), T(mx), T(w1), T(w2), T(w3),
+                          T(b1), T(b2), T(b3), Co, combin, B, radius, scaleInv, avg)
+    assert tuple(gout.shape) == oout.shape
+    err = rel_err(A(gout), oout, atol_scale=1e-5)
+    assert err <= RTOL, err
+    if e["R"] is not None:
+        rout = e["R"].spatial_conv(T(sp), T(sf), T(sb), T(pdf), T(smp), T(start), T(pairs), T(mn), T(mx), T(w1),
+                                   T(w2), T(w3), T(b1), T(b2), T(b3), Co, combin, B, radius, scaleInv, avg)
+        # the reference's own float atomics sit ~1e-6 from the order-free value; compare both to it
+        err_ref = rel_err(A(rout), oout, atol_scale=1e-5)
+        err_mine = rel_err(A(gout), A(rout), atol_scale=1e-5)
+        assert err_mine <= RTOL + err_ref, (err_mine, err_ref)
+
+
+def test_feature_permutations(env):
+    e = env
+    O, M, T, A = e["O"], e["M"], e["T"], e["A"]
+    rng = np.random.default_rng(0)
+    for N, C in ((1000, 1), (777, 3), (4096, 64), (513, 128)):
+        f = rng.uniform(-1, 1, (N, C)).astype(np.float32)
+        perm = rng.permutation(N).astype(np.int32)
+        assert np.array_equal(A(M.sort_features(T(f), T(perm))), O.sort_features(f, perm))
+        assert np.array_equal(A(M.sort_features_back(T(f), T(perm))), O.sort_features_back(f, perm))
+        back = M.sort_features_back(M.sort_features(T(f), T(perm)), T(perm))
+        assert np.array_equal(A(back), f)  # round trip
+
+
+def test_edge_cases(env):
+    e = env
+    O, M, T, A, torch = e["O"], e["M"], e["T"], e["A"], e["torch"]
+    # batch declared larger than the clouds present (eval builds the graph with batchSize 32 and feeds one cloud)
+    pts, bids, feats = make_batch(1, 512, "sphere", seed=8)
+    gmn, gmx = M.compute_aabb(T(pts), T(bids), 4, True)
+    omn, omx = O.compute_aabb(pts, bids, 4, True)
+    assert np.array_equal(A(gmn), omn) and np.array_equal(A(gmx), omx)
+    # a sample with no neighbour produces a zero output row and an empty CSR row
+    mn, mx, keys, idx, sp, sb, sf, cells = _grid(e, pts, bids, feats, 1, 0.05, True, O)
+    far = np.array([[0.0, 0.0, 0.0]], np.float32)  # centre of the sphere: nothing within 0.05
+    fb = np.zeros((1, 1), np.int32)
+    gs, gp = M.find_neighbors(T(far), T(fb), T(sp), T(cells), T(mn), T(mx), 0.05, 1, True)
+    assert gp.shape[0] == 0 and A(gs).tolist() == [[0]]
+    # invalid attributes raise like OP_REQUIRES
+    with pytest.raises(ValueError):
+        M.find_neighbors(T(far), T(fb), T(sp), T(cells), T(mn), T(mx), -1.0, 1, True)
+    with pytest.raises(ValueError):
+        M.compute_aabb(T(pts), T(bids), 0, True)
+    with pytest.raises(ValueError):
+        M.sort_features(T(feats), T(np.zeros((3,), np.int32)))
