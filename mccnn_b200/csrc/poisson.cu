@@ -2,42 +2,71 @@
 //
 // Replaces samplePointCloud / selectSamples / copyPoints (tf_ops/poisson_sampling.cu:51-124,175-244).  The
 // reference launches one tiny kernel per (cloud, phase) -- B*27 sequential launches (864 at B = 32), one thread per
-// cell walking 27 cells serially -- then blocks the host on the sample count.  Here:
-//   select  : ONE launch for the whole batch, one CTA per cloud, the 27 colour phases run inside the kernel
-//             separated by __syncthreads(); a warp owns a cell of the phase, its lanes own the 27 neighbour cells,
-//             the accepted flags of the cloud live in shared memory.  The accepted SET is identical to the
-//             reference's (it is deterministic there too: same-phase cells are >= 3 cells apart and a thread only
-//             flags points of its own cell).
-//   compact : the reference's output order inside a (cloud, phase) launch is atomic-arrival order; the canonical
-//             order (ascending position in the sorted array == ascending cell, then point) is produced by a
-//             counting sort on the 27*B (cloud, phase) buckets.  The sample count stays on the device.
+// cell walking its 27 neighbour cells serially -- then blocks the host on the sample count.  Here the whole op is ONE
+// kernel launch (plus one memset):
+//   * one CTA per cloud (clouds claimed through a ticket so that CTA order == cloud order); the 27 colour phases run
+//     inside the kernel separated by __syncthreads(); the accepted flags of the cloud live in shared memory;
+//   * a WARP owns a cell of the phase.  It first compacts the already-accepted points of the 26 neighbour cells into
+//     a small shared-memory list (lanes = neighbour cells), then tests its own points against that list with one
+//     point per lane, and finally resolves the order dependence INSIDE the cell (a point is rejected by an earlier
+//     accepted point of the same cell) with a short shuffle loop -- so the serial chain is the cell population, not
+//     the 27-cell neighbourhood population x memory latency;
+//   * the accepted set is identical to the reference's (deterministic there too: same-phase cells are >= 3 cells
+//     apart and a thread only flags points of its own cell);
+//   * output order: the reference's is atomic-arrival order inside a (cloud, phase) launch; the canonical order
+//     (cloud, phase, ascending position in the sorted array) is produced in-kernel by a stable per-phase
+//     compaction, and clouds are concatenated through a chained prefix (each CTA waits for its predecessor's
+//     running total only after all of its own work is done).  The sample count stays on the device.
 #include "common.cuh"
-#include "scan.cuh"
+#include "lookback.cuh"
 
 namespace mc {
 namespace {
 
 constexpr int kSelThreads = 512;
-constexpr int kSelFlagBytes = 64 * 1024;  // per-cloud accepted flags kept in shared memory up to this many points
-constexpr int kPtThreads = 256;
+constexpr int kSelWarps = kSelThreads / 32;
+constexpr int kSelFlagBytes = 48 * 1024;  // per-cloud accepted flags kept in shared memory up to this many points
+constexpr int kListCap = 128;             // accepted neighbour candidates a warp keeps in shared memory
+constexpr int kSelfOffset = 17;           // index of (0,0,0) in kOffsPool
+
+struct SelShared {
+    float4 list[kSelWarps][kListCap];
+    int listIdx[kSelWarps][kListCap];
+    int listCount[kSelWarps];
+    int warpCnt[kSelWarps][28];
+    int phaseBase[28];
+    int running[28];
+    int lo, hi, cloud, base;
+};
+
+__device__ __forceinline__ bool within_pq(float px, float py, float pz, float qx, float qy, float qz, float r) {
+    return within_radius(px, py, pz, qx, qy, qz, r);
+}
 
 __global__ void __launch_bounds__(kSelThreads)
-    poisson_select_kernel(bool scaleInv, float radius, int n, const float* __restrict__ mn,
-                          const float* __restrict__ mx, const float* __restrict__ pts,
-                          const int2* __restrict__ cellIdx, unsigned char* sel) {
-    extern __shared__ unsigned char sFlags[];
-    __shared__ int sLo, sHi;
-    const int b = blockIdx.x;
-    const int lane = lane_id(), warp = threadIdx.x >> 5, numWarps = kSelThreads / 32;
+    poisson_kernel(bool scaleInv, float radius, int B, int n, const float* __restrict__ mn,
+                   const float* __restrict__ mx, const float* __restrict__ pts, const int2* __restrict__ cellIdx,
+                   unsigned char* selGlobal, int* __restrict__ tmpIdx, unsigned long long* chain, int capOut,
+                   float* __restrict__ outPts, int* __restrict__ outBids, int* __restrict__ outIdx,
+                   int* __restrict__ dNumSamples, int* __restrict__ dOverflow) {
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    SelShared& sh = *reinterpret_cast<SelShared*>(smemRaw);
+    unsigned char* sFlags = smemRaw + sizeof(SelShared);
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    const unsigned ltMask = (1u << lane) - 1u;
+
+    // claim a cloud: ticket order == start order, so waiting on the predecessor at the end cannot deadlock
+    if (threadIdx.x == 0) {
+        sh.cloud = lookback_ticket(chain);
+        sh.lo = INT_MAX;
+        sh.hi = 0;
+    }
+    __syncthreads();
+    const int b = sh.cloud;
     const int cellsPerCloud = n * n * n;
     const int2* cells = cellIdx + (size_t)b * cellsPerCloud;
 
     // extent of this cloud inside the sorted array (the sort is batch-major)
-    if (threadIdx.x == 0) {
-        sLo = INT_MAX;
-        sHi = 0;
-    }
-    __syncthreads();
     {
         int lo = INT_MAX, hi = 0;
         for (int c = threadIdx.x; c < cellsPerCloud; c += kSelThreads) {
@@ -50,134 +79,187 @@ __global__ void __launch_bounds__(kSelThreads)
         lo = __reduce_min_sync(MC_FULL_MASK, lo);
         hi = __reduce_max_sync(MC_FULL_MASK, hi);
         if (lane == 0) {
-            atomicMin(&sLo, lo);
-            atomicMax(&sHi, hi);
+            atomicMin(&sh.lo, lo);
+            atomicMax(&sh.hi, hi);
         }
     }
     __syncthreads();
-    const int cLo = sLo, cHi = sHi;
+    const int cLo = sh.lo, cHi = sh.hi;
     const int nCloud = cHi > cLo ? cHi - cLo : 0;
-    if (nCloud == 0) return;
     const bool inSmem = nCloud <= kSelFlagBytes;
+    // flags addressed by sorted position; volatile: written and read by different warps between barriers
+    volatile unsigned char* flags = inSmem ? (sFlags - cLo) : selGlobal;
     if (inSmem)
         for (int t = threadIdx.x; t < nCloud; t += kSelThreads) sFlags[t] = 0;
+    if (threadIdx.x < 28) {
+        sh.phaseBase[threadIdx.x] = 0;
+        sh.running[threadIdx.x] = 0;
+    }
     __syncthreads();
 
     const float ext = max_extent(mn, mx, b);
     const float r = scaleInv ? __fmul_rn(radius, ext) : radius;
 
-    for (int ph = 0; ph < 27; ++ph) {
-        const int ox = kOffsPool[ph][0], oy = kOffsPool[ph][1], oz = kOffsPool[ph][2];
-        // cells of this phase: 3t+1+o < n  (only the upper bound exists, poisson_sampling.cu:70-74)
-        const int tX = (n + 1 - ox) / 3, tY = (n + 1 - oy) / 3, tZ = (n + 1 - oz) / 3;
-        const int total = tX * tY * tZ;
-        for (int c = warp; c < total; c += numWarps) {
-            const int tx = c / (tY * tZ), rem = c - tx * (tY * tZ);
-            const int ty = rem / tZ, tz = rem - ty * tZ;
-            const int x = tx * 3 + 1 + ox, y = ty * 3 + 1 + oy, z = tz * 3 + 1 + oz;
-            const int2 own = cells[(x * n + y) * n + z];
-            if (own.y <= own.x) continue;
-            int nlo = 0, nhi = 0;
-            if (lane < 27) {
-                int qx = x + kOffsPool[lane][0], qy = y + kOffsPool[lane][1], qz = z + kOffsPool[lane][2];
-                if (qx >= 0 && qx < n && qy >= 0 && qy < n && qz >= 0 && qz < n) {
-                    int2 ce = cells[(qx * n + qy) * n + qz];
-                    nlo = ce.x;
-                    nhi = ce.y;
-                }
-            }
-            for (int i = own.x; i < own.y; ++i) {
-                const float px = pts[(size_t)i * 3], py = pts[(size_t)i * 3 + 1], pz = pts[(size_t)i * 3 + 2];
-                bool coll = false;
-                for (int j = nlo; j < nhi; ++j) {
-                    unsigned char fl = inSmem ? sFlags[j - cLo] : __ldcg(&sel[j]);
-                    if (fl && within_radius(px, py, pz, pts[(size_t)j * 3], pts[(size_t)j * 3 + 1],
-                                            pts[(size_t)j * 3 + 2], r)) {
-                        coll = true;
-                        break;
+    if (nCloud > 0) {
+        for (int ph = 0; ph < 27; ++ph) {
+            const int ox = kOffsPool[ph][0], oy = kOffsPool[ph][1], oz = kOffsPool[ph][2];
+            // cells of this phase: 3t+1+o < n  (only the upper bound exists, poisson_sampling.cu:70-74)
+            const int tX = (n + 1 - ox) / 3, tY = (n + 1 - oy) / 3, tZ = (n + 1 - oz) / 3;
+            const int total = tX * tY * tZ;
+            for (int c = warp; c < total; c += kSelWarps) {
+                const int tx = c / (tY * tZ), rem = c - tx * (tY * tZ);
+                const int ty = rem / tZ, tz = rem - ty * tZ;
+                const int x = tx * 3 + 1 + ox, y = ty * 3 + 1 + oy, z = tz * 3 + 1 + oz;
+                const int2 own = cells[(x * n + y) * n + z];
+                if (own.y <= own.x) continue;
+
+                // ---- A: compact the accepted points of the 26 neighbour cells into the warp's list
+                int nlo = 0, nhi = 0;
+                if (lane < 27 && lane != kSelfOffset) {
+                    int qx = x + kOffsPool[lane][0], qy = y + kOffsPool[lane][1], qz = z + kOffsPool[lane][2];
+                    if (qx >= 0 && qx < n && qy >= 0 && qy < n && qz >= 0 && qz < n) {
+                        int2 ce = cells[(qx * n + qy) * n + qz];
+                        nlo = ce.x;
+                        nhi = ce.y;
                     }
                 }
-                if (!__any_sync(MC_FULL_MASK, coll) && lane == 0) {
-                    if (inSmem)
-                        sFlags[i - cLo] = (unsigned char)(ph + 1);
-                    else
-                        __stcg(&sel[i], (unsigned char)(ph + 1));
+                if (lane == 0) sh.listCount[warp] = 0;
+                __syncwarp();
+                for (int j = nlo; j < nhi; ++j)
+                    if (flags[j]) {
+                        int slot = atomicAdd(&sh.listCount[warp], 1);
+                        if (slot < kListCap) sh.listIdx[warp][slot] = j;
+                    }
+                __syncwarp();
+                int L = sh.listCount[warp];
+                bool listOk = L <= kListCap;  // else: fall back to walking the cells directly (never wrong, only slow)
+                if (listOk) {
+                    for (int t = lane; t < L; t += 32) {
+                        int j = sh.listIdx[warp][t];
+                        sh.list[warp][t] =
+                            make_float4(pts[(size_t)j * 3], pts[(size_t)j * 3 + 1], pts[(size_t)j * 3 + 2], 0.f);
+                    }
                 }
                 __syncwarp();
+
+                // ---- B: own points, 32 at a time, one per lane
+                for (int c0 = own.x; c0 < own.y; c0 += 32) {
+                    const int i = c0 + lane;
+                    const bool valid = i < own.y;
+                    float px = 0.f, py = 0.f, pz = 0.f;
+                    if (valid) {
+                        px = pts[(size_t)i * 3];
+                        py = pts[(size_t)i * 3 + 1];
+                        pz = pts[(size_t)i * 3 + 2];
+                    }
+                    bool blocked = false;  // an accepted point of an earlier phase / earlier chunk lies within r
+                    if (listOk) {
+                        for (int t = 0; t < L; ++t) {
+                            float4 q = sh.list[warp][t];
+                            blocked |= within_pq(px, py, pz, q.x, q.y, q.z, r);
+                        }
+                    } else {
+                        for (int o = 0; o < 27; ++o) {
+                            int lo2 = __shfl_sync(MC_FULL_MASK, nlo, o), hi2 = __shfl_sync(MC_FULL_MASK, nhi, o);
+                            if (o == kSelfOffset) {  // earlier chunks of the own cell
+                                lo2 = own.x;
+                                hi2 = c0;
+                            }
+                            for (int j = lo2; j < hi2; ++j)
+                                if (flags[j])
+                                    blocked |= within_pq(px, py, pz, pts[(size_t)j * 3], pts[(size_t)j * 3 + 1],
+                                                         pts[(size_t)j * 3 + 2], r);
+                        }
+                    }
+                    // order dependence inside the chunk: point u is rejected by an accepted earlier point within r
+                    const int cnt = min(32, own.y - c0);
+                    bool mySel = false;
+                    for (int u = 0; u < cnt; ++u) {
+                        float ux = __shfl_sync(MC_FULL_MASK, px, u);
+                        float uy = __shfl_sync(MC_FULL_MASK, py, u);
+                        float uz = __shfl_sync(MC_FULL_MASK, pz, u);
+                        int ub = __shfl_sync(MC_FULL_MASK, (int)blocked, u);
+                        bool hit = lane < u && mySel && within_pq(ux, uy, uz, px, py, pz, r);
+                        unsigned any = __ballot_sync(MC_FULL_MASK, hit);
+                        if (lane == u) mySel = (ub == 0) && (any == 0);
+                    }
+                    if (valid && mySel) flags[i] = (unsigned char)(ph + 1);
+                    if (c0 + 32 < own.y && listOk) {  // later chunks of this cell must see this chunk's accepted points
+                        unsigned selMask = __ballot_sync(MC_FULL_MASK, valid && mySel);
+                        int pos = L + __popc(selMask & ltMask);
+                        if (valid && mySel && pos < kListCap) sh.list[warp][pos] = make_float4(px, py, pz, 0.f);
+                        L += __popc(selMask);
+                        if (L > kListCap) listOk = false;
+                    }
+                    __syncwarp();
+                }
             }
+            __syncthreads();
+        }
+
+        // ---- stable compaction by (phase, position): tmpIdx[cLo + rank] = position
+        for (int t = threadIdx.x; t < nCloud; t += kSelThreads) {
+            int f = flags[cLo + t];
+            if (f) atomicAdd(&sh.phaseBase[f], 1);  // histogram at [f] so that the exclusive scan lands at [f-1]...
         }
         __syncthreads();
+        if (threadIdx.x == 0) {  // phaseBase[f] <- number of accepted points in phases < f-1 ... i.e. exclusive scan
+            int run = 0;
+            for (int f = 1; f <= 27; ++f) {
+                int cntF = sh.phaseBase[f];
+                sh.phaseBase[f] = run;
+                run += cntF;
+            }
+            sh.phaseBase[0] = run;  // total accepted points of the cloud
+        }
+        __syncthreads();
+        for (int t0 = 0; t0 < nCloud; t0 += kSelThreads) {
+            for (int e = threadIdx.x; e < kSelWarps * 28; e += kSelThreads) (&sh.warpCnt[0][0])[e] = 0;
+            __syncthreads();
+            const int t = t0 + threadIdx.x;
+            const int f = t < nCloud ? flags[cLo + t] : 0;
+            const unsigned grp = __match_any_sync(MC_FULL_MASK, f);
+            if (f && lane == __ffs(grp) - 1) sh.warpCnt[warp][f] = __popc(grp);
+            __syncthreads();
+            if (f) {
+                int pos = sh.phaseBase[f] + sh.running[f] + __popc(grp & ltMask);
+                for (int w = 0; w < warp; ++w) pos += sh.warpCnt[w][f];
+                tmpIdx[cLo + pos] = cLo + t;
+            }
+            __syncthreads();
+            if (threadIdx.x >= 1 && threadIdx.x <= 27) {
+                int add = 0;
+                for (int w = 0; w < kSelWarps; ++w) add += sh.warpCnt[w][threadIdx.x];
+                sh.running[threadIdx.x] += add;
+            }
+            __syncthreads();
+        }
     }
-    if (inSmem)
-        for (int t = threadIdx.x; t < nCloud; t += kSelThreads) sel[cLo + t] = sFlags[t];
-}
+    const int mCloud = nCloud > 0 ? sh.phaseBase[0] : 0;
 
-// (cloud, phase) histogram; arrival[i] = arrival rank inside the bucket
-__global__ void __launch_bounds__(kPtThreads) poisson_count_kernel(const int* __restrict__ dN, int cap, int B,
-                                                                   const unsigned char* __restrict__ sel,
-                                                                   const int* __restrict__ bids,
-                                                                   int* __restrict__ counters,
-                                                                   int* __restrict__ arrival) {
-    const int N = live_count(dN, cap);
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    int ph = sel[i];
-    if (ph == 0) return;
-    int b = bids[i];
-    b = (unsigned)b < (unsigned)B ? b : 0;
-    arrival[i] = atomicAdd(&counters[b * 27 + ph - 1], 1);
-}
-
-__global__ void __launch_bounds__(kPtThreads) poisson_bucket_kernel(const int* __restrict__ dN, int cap, int B,
-                                                                    const unsigned char* __restrict__ sel,
-                                                                    const int* __restrict__ bids,
-                                                                    const int* __restrict__ local,
-                                                                    const int* __restrict__ tileOffs,
-                                                                    const int* __restrict__ arrival,
-                                                                    int* __restrict__ bucket) {
-    const int N = live_count(dN, cap);
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    int ph = sel[i];
-    if (ph == 0) return;
-    int b = bids[i];
-    b = (unsigned)b < (unsigned)B ? b : 0;
-    bucket[scan_prefix(local, tileOffs, b * 27 + ph - 1) + arrival[i]] = i;
-}
-
-__global__ void __launch_bounds__(kPtThreads) poisson_emit_kernel(const int* __restrict__ dN, int cap, int B,
-                                                                  const unsigned char* __restrict__ sel,
-                                                                  const int* __restrict__ bids,
-                                                                  const float* __restrict__ pts,
-                                                                  const int* __restrict__ local,
-                                                                  const int* __restrict__ tileOffs,
-                                                                  const int* __restrict__ dTotal,
-                                                                  const int* __restrict__ bucket, int capOut,
-                                                                  int* __restrict__ dOverflow,
-                                                                  float* __restrict__ outPts,
-                                                                  int* __restrict__ outBids, int* __restrict__ outIdx) {
-    const int N = live_count(dN, cap);
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    int ph = sel[i];
-    if (ph == 0) return;
-    int b = bids[i];
-    b = (unsigned)b < (unsigned)B ? b : 0;
-    int k = b * 27 + ph - 1;
-    int beg = scan_prefix(local, tileOffs, k);
-    int end = (k + 1 < B * 27) ? scan_prefix(local, tileOffs, k + 1) : *dTotal;
-    int rnk = 0;
-    for (int p = beg; p < end; ++p) rnk += (bucket[p] < i);
-    int pos = beg + rnk;
-    if (pos >= capOut) {
-        if (dOverflow != nullptr) *dOverflow = 1;
-        return;
+    // ---- exclusive prefix of the per-cloud sample counts (decoupled look-back, lookback.cuh)
+    if (warp == 0) {
+        int base = lookback_exclusive_prefix(chain, b, mCloud);
+        if (lane == 0) {
+            if (b == B - 1) *dNumSamples = base + mCloud;
+            sh.base = base;
+        }
     }
-    outPts[(size_t)pos * 3] = pts[(size_t)i * 3];
-    outPts[(size_t)pos * 3 + 1] = pts[(size_t)i * 3 + 1];
-    outPts[(size_t)pos * 3 + 2] = pts[(size_t)i * 3 + 2];
-    outBids[pos] = b;
-    outIdx[pos] = i;
+    __syncthreads();
+    const int base = sh.base;
+    for (int t = threadIdx.x; t < mCloud; t += kSelThreads) {
+        const int i = tmpIdx[cLo + t];
+        const int pos = base + t;
+        if (pos >= capOut) {
+            if (dOverflow != nullptr) *dOverflow = 1;
+            continue;
+        }
+        outPts[(size_t)pos * 3] = pts[(size_t)i * 3];
+        outPts[(size_t)pos * 3 + 1] = pts[(size_t)i * 3 + 1];
+        outPts[(size_t)pos * 3 + 2] = pts[(size_t)i * 3 + 2];
+        outBids[pos] = b;
+        outIdx[pos] = i;
+    }
 }
 
 }  // namespace
@@ -185,49 +267,44 @@ __global__ void __launch_bounds__(kPtThreads) poisson_emit_kernel(const int* __r
 
 using namespace mc;
 
-// workspace ints: sel bytes (N/4+1) | counters[27B] | tileSums | arrival[N] | bucket[N]
+// workspace ints: look-back descriptors (2 * (B + 2)) | flag bytes (N/4 + 1 ints) | tmpIdx[N]
 extern "C" long long mc_poisson_workspace_ints(int numPoints, int batchSize) {
     long long N = numPoints > 0 ? numPoints : 1;
-    return (N / 4 + 1) + 27LL * batchSize + scan_num_tiles(27 * batchSize) + 2 * N + 8;
+    return 2LL * (batchSize + 2) + (N / 4 + 1) + N + 8;
 }
 
 // samplePointCloud + copyPoints, tf_ops/poisson_sampling.cu:175-244.  Outputs hold capacityOut rows (numPoints
 // always suffices); the live number of samples is written to *dNumSamples (device); samples past the capacity are
-// dropped and *dOverflow (optional) is set.
+// dropped and *dOverflow (optional) is set.  numPoints / dNumPoints only size the workspace: the live extent of every
+// cloud is read from the cell table.
 extern "C" int mc_poisson_sampling(int scaleInv, float radius, int numPoints, const int* dNumPoints, int batchSize,
                                    int numCells, const float* aabbMin, const float* aabbMax, const float* pts,
                                    const int* batchIds, const int* cellIdx, int* workspace, int capacityOut,
                                    float* outPts, int* outBatchIds, int* outIdx, int* dNumSamples, int* dOverflow,
                                    void* stream) {
+    (void)dNumPoints;
+    (void)batchIds;
     MC_REQUIRE(radius > 0.0f, "mc_poisson_sampling: radius must be positive");
     MC_REQUIRE(batchSize > 0 && numCells > 0, "mc_poisson_sampling: batch size and cell count must be positive");
     MC_REQUIRE(dNumSamples != nullptr, "mc_poisson_sampling: dNumSamples required");
     cudaStream_t s = (cudaStream_t)stream;
+    const size_t smem = sizeof(SelShared) + kSelFlagBytes;
     static bool attrSet = false;
     if (!attrSet) {
-        cudaFuncSetAttribute(poisson_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSelFlagBytes);
+        cudaFuncSetAttribute(poisson_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attrSet = true;
     }
     const long long N = numPoints > 0 ? numPoints : 1;
-    const int nb = 27 * batchSize;
-    unsigned char* sel = reinterpret_cast<unsigned char*>(workspace);
-    int* counters = workspace + (N / 4 + 1);
-    int* tileSums = counters + nb;
-    int* arrival = tileSums + scan_num_tiles(nb);
-    int* bucket = arrival + N;
-    cudaMemsetAsync(workspace, 0, sizeof(int) * (size_t)((N / 4 + 1) + nb), s);  // sel + counters
+    MC_REQUIRE(((uintptr_t)workspace) % 8 == 0, "mc_poisson_sampling: workspace must be 8-byte aligned");
+    const int descInts = 2 * (batchSize + 2);
+    unsigned long long* chain = reinterpret_cast<unsigned long long*>(workspace);
+    unsigned char* sel = reinterpret_cast<unsigned char*>(workspace + descInts);
+    int* tmpIdx = workspace + descInts + (N / 4 + 1);
+    cudaMemsetAsync(workspace, 0, sizeof(int) * (size_t)(descInts + (N / 4 + 1)), s);  // descriptors + flags
     if (numPoints > 0) {
-        poisson_select_kernel<<<batchSize, kSelThreads, kSelFlagBytes, s>>>(
-            scaleInv != 0, radius, numCells, aabbMin, aabbMax, pts, reinterpret_cast<const int2*>(cellIdx), sel);
-        int grid = cdiv(numPoints, kPtThreads);
-        poisson_count_kernel<<<grid, kPtThreads, 0, s>>>(dNumPoints, numPoints, batchSize, sel, batchIds, counters,
-                                                         arrival);
-        launch_scan(counters, nullptr, nb, tileSums, dNumSamples, s);
-        poisson_bucket_kernel<<<grid, kPtThreads, 0, s>>>(dNumPoints, numPoints, batchSize, sel, batchIds, counters,
-                                                          tileSums, arrival, bucket);
-        poisson_emit_kernel<<<grid, kPtThreads, 0, s>>>(dNumPoints, numPoints, batchSize, sel, batchIds, pts,
-                                                        counters, tileSums, dNumSamples, bucket, capacityOut,
-                                                        dOverflow, outPts, outBatchIds, outIdx);
+        poisson_kernel<<<batchSize, kSelThreads, smem, s>>>(
+            scaleInv != 0, radius, batchSize, numCells, aabbMin, aabbMax, pts, reinterpret_cast<const int2*>(cellIdx),
+            sel, tmpIdx, chain, capacityOut, outPts, outBatchIds, outIdx, dNumSamples, dOverflow);
     } else {
         cudaMemsetAsync(dNumSamples, 0, sizeof(int), s);
     }

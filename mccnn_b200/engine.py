@@ -68,6 +68,8 @@ class PlannedForward:
         if self.plan is None or key != self._shape_key:
             out = self._record(pts, bids, feats)
             return out, torch.zeros((1,), dtype=torch.int32, device=pts.device)
+        if self.plan.overflow is None:
+            self.plan.begin(pts.device)
         self.plan.overflow.zero_()
         if not self.use_graph:
             out = self._planned(pts, bids, feats)

@@ -150,7 +150,8 @@ def get_sampled_features(inSampledIndexs, pInFeatures):
 
 def spatial_conv(inPts, inFeatures, inBatchIds, inPDFs, inSamplePts, neighStartIndexs, packedNeighs, aabbMin, aabbMax,
                  weights1, weights2, weightsOut, biases1, biases2, biasesOut, numOutFeatures, combin, batchSize,
-                 radius, scaleInv, avg, accum_double=False):
+                 radius, scaleInv, avg, accum_double=False, abs_sum=False):
+    """accum_double: float64 accumulation; abs_sum: return sum |contribution| per output (error scale)."""
     pts, feats, bids = _f(inPts), _f(inFeatures), _i(inBatchIds).reshape(-1)
     pdfs, samples = _f(inPDFs).reshape(-1), _f(inSamplePts)
     start, pairs, mn, mx = _i(neighStartIndexs).reshape(-1), _i(packedNeighs), _f(aabbMin), _f(aabbMax)
@@ -161,5 +162,5 @@ def spatial_conv(inPts, inFeatures, inBatchIds, inPDFs, inSamplePts, neighStartI
     lib().orc_spatial_conv(_ci(int(avg)), _ci(int(scaleInv)), _ci(K), _ci(C), _ci(numOutFeatures), _ci(M),
                            _ci(int(combin)), _cf(radius), _p(pts), _p(bids), _p(feats), _p(pdfs), _p(samples),
                            _p(start), _p(pairs), _p(mn), _p(mx), _p(w1), _p(b1), _p(w2), _p(b2), _p(wo), _p(bo),
-                           _ci(int(accum_double)), _p(out))
+                           _ci(2 if abs_sum else int(accum_double)), _p(out))
     return out

@@ -322,7 +322,10 @@ void orc_get_sampled_features(int M, int C, const int *idx, const float *feats, 
  *     Weight buffers are the flat reinterpretations the kernel uses (spatial_conv.cu:49-73,172):
  *       W1[(8q+t)*3+a], b1[8q+t], W2[q*64+t*8+u], b2[8q+t], Wo[(8q+t)*8+u], bo[8q+t].
  *     accumDouble = 0: float accumulation in pair order (one valid ordering of the reference's float
- *     atomics); 1: double accumulation (the order-free value both sides must approach).
+ *     atomics); 1: double accumulation (the order-free value both sides must approach); 2: the sum of the
+ *     ABSOLUTE contributions per output (the scale against which a float32 sum's error is measured: outputs are
+ *     signed sums that cancel, so an error relative to the result itself is unbounded for any summation order,
+ *     the reference's included).
  * ---------------------------------------------------------------------------------------------- */
 void orc_spatial_conv(int avg, int scaleInv, int K, int C, int Co, int M, int combin, float radius,
                       const float *pts, const int *bids, const float *feats, const float *pdfs,
@@ -367,7 +370,7 @@ void orc_spatial_conv(int avg, int scaleInv, int K, int C, int Co, int M, int co
                 int c = nr % C;
                 int o = combin ? nr / C : c;
                 float contrib = (feats[(size_t)j * C + c] * a) / w;
-                acc[(size_t)i * outC + o] += (double)contrib;
+                acc[(size_t)i * outC + o] += accumDouble == 2 ? fabs((double)contrib) : (double)contrib;
                 accf[(size_t)i * outC + o] += contrib;
             }
         }

@@ -73,3 +73,14 @@ def rel_err(a, b, atol_scale=1e-6):
         return 0.0
     atol = atol_scale * (np.abs(b).max() if b.size else 1.0)
     return float((np.abs(a - b) / (np.maximum(np.abs(a), np.abs(b)) + atol)).max())
+
+
+def sum_err(a, b, scale):
+    """max |a-b| / scale, scale = sum of |terms| behind each element: the relative error of a float32 SUM.
+    (Outputs of spatial_conv are signed sums that cancel; see oracle/mccnn_oracle.c orc_spatial_conv.)"""
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    s = np.asarray(scale, np.float64)
+    if a.size == 0:
+        return 0.0
+    return float((np.abs(a - b) / (s + 1e-30 + 1e-12 * s.max())).max())

@@ -10,7 +10,7 @@ launch) the comparison is on the canonicalised form -- see oracle/mccnn_oracle.c
 import numpy as np
 import pytest
 
-from common import make_batch, make_conv_weights, rel_err
+from common import make_batch, make_conv_weights, rel_err, sum_err
 
 pytestmark = pytest.mark.gpu
 
@@ -62,7 +62,8 @@ def test_aabb_sort_bit_exact(env, B, N, dist, ragged, radius, scaleInv):
     names = ["aabbMin", "aabbMax", "keys", "indexs", "sortPts", "sortBatchIds", "sortFeatures", "cellIndexs"]
     for name, a, b in zip(names, g, o):
         assert np.array_equal(e["A"](a).reshape(-1), np.asarray(b).reshape(-1)), name
-    if e["R"] is not None and pts.shape[0] % 256 == 0:  # reference aabb has a last-block smem bug otherwise
+    tail = pts.shape[0] % 256  # reference aabb leaves smem rows uninitialised when 0 < N % 256 < B (aabb_gpu.cu:69-78)
+    if e["R"] is not None and (tail == 0 or tail >= B):
         R, T, A = e["R"], e["T"], e["A"]
         tb = T(bids)
         rmn, rmx = R.compute_aabb(T(pts), tb, B, scaleInv)
@@ -182,15 +183,23 @@ def test_spatial_conv(env, B, N, dist, C, Co, combin, radius, avg, scaleInv):
     gout = M.spatial_conv(T(sp), T(sf), T(sb), T(pdf), T(smp), T(start), T(pairs), T(mn), T(mx), T(w1), T(w2), T(w3),
                           T(b1), T(b2), T(b3), Co, combin, B, radius, scaleInv, avg)
     assert tuple(gout.shape) == oout.shape
-    err = rel_err(A(gout), oout, atol_scale=1e-5)
+    # an output is a signed float32 sum over neighbours x input features: its error is measured against the sum of
+    # the absolute contributions (any summation order, the reference's atomics included, is only accurate on that
+    # scale); elements that do not cancel are additionally held to the plain 1e-5 relative bound.
+    scale = O.spatial_conv(sp, sf, sb, pdf, smp, start, pairs, mn, mx, w1, w2, w3, b1, b2, b3, Co, combin, B, radius,
+                           scaleInv, avg, abs_sum=True)
+    err = sum_err(A(gout), oout, scale)
     assert err <= RTOL, err
+    big = np.abs(oout) >= 0.1 * scale
+    if big.any():
+        assert rel_err(A(gout)[big], oout[big], atol_scale=0.0) <= 10 * RTOL
     if e["R"] is not None:
         rout = e["R"].spatial_conv(T(sp), T(sf), T(sb), T(pdf), T(smp), T(start), T(pairs), T(mn), T(mx), T(w1),
                                    T(w2), T(w3), T(b1), T(b2), T(b3), Co, combin, B, radius, scaleInv, avg)
-        # the reference's own float atomics sit ~1e-6 from the order-free value; compare both to it
-        err_ref = rel_err(A(rout), oout, atol_scale=1e-5)
-        err_mine = rel_err(A(gout), A(rout), atol_scale=1e-5)
-        assert err_mine <= RTOL + err_ref, (err_mine, err_ref)
+        err_vs_ref = sum_err(A(gout), A(rout), scale)
+        err_ref = sum_err(A(rout), oout, scale)   # the reference's own distance from the order-free value
+        assert err_vs_ref <= RTOL, (err_vs_ref, err_ref)
+        assert err <= max(2 * err_ref, 2e-6), (err, err_ref)  # and we are not less accurate than the reference
 
 
 def test_feature_permutations(env):
