@@ -1,0 +1,470 @@
+#!/usr/bin/env python
+"""bench.py -- MCClassS forward points/s on synthetic 32 x 1024-point clouds (BASELINE.json metric, configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A step = one MCClassS forward (models/MCClassS.py topology: 3-level Poisson hierarchy, 3 Monte-Carlo convolutions,
+dense glue, 40 logits per cloud) over one packed batch of 32 clouds x 1024 points per GPU.  Multi-GPU: independent
+clouds sharded over the ranks (32 clouds per GPU, weak scaling), ONE NCCL all_gather of the per-cloud logits per step.
+
+One JSON line on rank 0:
+  value   points/s, whole job, batches already resident in HBM, CUDA-graph replay, CUDA-event timed per step
+          (L2 flushed between steps, outside the timed intervals), max over ranks;
+  e2e     the same metric through the host-facing call (pinned host buffers -> H2D -> forward -> D2H logits),
+          wall clock around every call;
+  roofline   dominant kernel of the step: algorithmic bytes / its mean CUDA-event duration,
+             against the measured HBM copy bandwidth in MEASURED_PEAKS.json;
+  cpu_baseline  the oracle port of the same forward on the host (1 thread) + NumPy spatial_conv of config 1;
+`--impl reference` runs the reference's own CUDA kernels (oracle/_ref, built from /root/reference/tf_ops/*.cu) through
+the same op sequence with the reference's host choreography (oracle/ref_pipeline.py) -- the reference has no CPU
+implementation of this path; its GPU path re-compiled for sm_100a IS the reference arm.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from common import make_batch, make_conv_weights  # noqa: E402
+
+NUM_CAT = 40
+RADII = [0.1, 0.4, math.sqrt(3.0) + 0.1]
+CONV_RADII = [0.2, 0.8, math.sqrt(3.0) + 0.1]
+
+
+# ----------------------------------------------------------------------------------------------- utilities
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def algorithmic_bytes(op, call, sizes, B, k, n_in=1):
+    """SURVEY.md section 8(d) per-op byte counts for call number `call` of `op` inside one MCClassS forward."""
+    N = [sizes["N0"], sizes["M1"], sizes["M2"], sizes["M3"]]
+    K = [sizes["K1"], sizes["K2"], sizes["K3"]]
+    hier_n = [max(1, int(np.float32(1.0) / np.float32(r))) for r in RADII]
+    conv_n = [max(1, int(np.float32(1.0) / np.float32(r))) for r in CONV_RADII]
+    feat_c = [n_in, n_in, n_in]                      # features carried through the hierarchy
+    conv_c = [n_in, 2 * k, 4 * k]
+    conv_co = [k, 2 * k, 4 * k]
+    if op == "compute_aabb":
+        return 16 * N[0] + 24 * B
+    if op == "sort_points":                          # calls: hier L0, hier L1, hier L2, conv1, conv2, conv3
+        order = [("h", 0), ("h", 1), ("h", 2), ("c", 0), ("c", 1), ("c", 2)][call]
+        lvl = order[1]
+        n, C = (hier_n[lvl], feat_c[lvl]) if order[0] == "h" else (conv_n[lvl], conv_c[lvl])
+        return N[lvl] * (48 + 8 * C) + 20 * B * n ** 3
+    if op == "poisson_sampling":
+        return 13 * N[call] + 8 * B * hier_n[call] ** 3 + 20 * N[call + 1]
+    if op == "get_sampled_features":
+        return N[call + 1] * (4 + 8 * feat_c[call])
+    if op == "transform_indexs":
+        return 8 * N[call] + 8 * N[call + 1]
+    if op in ("find_neighbors_count", "find_neighbors_pack", "find_neighbors"):
+        M, Np, G = N[call + 1], N[call], B * conv_n[call] ** 3
+        full = 16 * M + 12 * Np + 8 * min(G, 27 * M) + 4 * M + 8 * K[call]
+        return full if op != "find_neighbors_count" else full - 8 * K[call]
+    if op == "compute_pdf":
+        return 12 * K[call] + 4 * N[call + 1] + 12 * N[call]
+    if op == "spatial_conv":
+        C, Co = conv_c[call], conv_co[call]
+        nOut = C * Co if call == 0 else C
+        nb = (nOut + 7) // 8
+        return (12 * K[call] + 4 * C * K[call] + 12 * N[call] + 12 * N[call + 1] + 4 * N[call + 1] +
+                4 * Co * N[call + 1] + 4 * (8 * nb * 13 + nOut * 9))
+    return 0
+
+
+def flush_l2(buf):
+    buf.add_(1.0)  # read + write a buffer larger than the 126 MB L2
+
+
+# ----------------------------------------------------------------------------------------------- our arm
+def run_ours(args, rank, world, dev):
+    import torch.distributed as dist
+    import mccnn_b200
+    from mccnn_b200 import ops, variables
+    from mccnn_b200._lib import lib
+    from mccnn_b200.engine import PlannedForward, HostForward, gather_logits
+    from mccnn_b200.models import MCClassS
+
+    B, P, k = args.batch, args.points, args.k
+    store = variables.VariableStore(device=dev, seed=0)
+
+    def fn(p, b, f):
+        return MCClassS.create_network(p, b, f, 1, B, k, NUM_CAT, False, 1.0, 1.0, store=store)
+
+    n_batches = 4
+    host = [make_batch(B, P, "sphere", seed=1000 * rank + i) for i in range(n_batches)]
+    pinned = [tuple(torch.from_numpy(a).pin_memory() for a in h) for h in host]
+    resident = [tuple(t.to(dev) for t in h) for h in pinned]
+
+    eng = PlannedForward(fn, B, use_graph=True, slack=1.3)
+    eng.calibrate(resident)
+    sizes = dict(zip(["M1", "M2", "M3", "K1", "K2", "K3"], eng.plan.sizes))
+    sizes["N0"] = B * P
+    flush = torch.zeros(192 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # 192 MiB > L2
+
+    def step(i):
+        out, flag = eng.run_async(*resident[i % n_batches])
+        if world > 1:
+            out = gather_logits(out, B * world, world)
+        return out, flag
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    torch.cuda.synchronize(dev)
+
+    # ---- value: device-resident inputs, per-step CUDA events, L2 flushed between steps
+    sampler = ClockSampler(dev.index)
+    sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    flags = torch.zeros((1,), dtype=torch.int32, device=dev)
+    launches0 = lib.mc_launch_count()
+    t_wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush_l2(flush)
+        starts[i].record()
+        out, flag = step(i)
+        ends[i].record()
+        flags += flag
+    torch.cuda.synchronize(dev)
+    t_wall = time.perf_counter() - t_wall0
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop()
+    per_step = [s.elapsed_time(e) for s, e in zip(starts, ends)]
+    ms_local = float(np.mean(per_step))
+    overflowed = int(flags.item())
+    t = torch.tensor([ms_local], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item())
+    value = B * P * world / (ms_per_step * 1e-3)
+
+    # ---- kernels per forward (ours) + per-op CUDA-event timing in eager planned mode (every op visible)
+    eager = PlannedForward(fn, B, use_graph=False, slack=1.3)
+    eager.plan, eager._shape_key = eng.plan, eng._shape_key
+    eager.run_async(*resident[0])
+    torch.cuda.synchronize(dev)
+    c0 = lib.mc_launch_count()
+    eager.run_async(*resident[0])
+    launches_per_forward = int(lib.mc_launch_count() - c0)
+    names = ["compute_aabb", "build_grid", "sort_points_step1", "sort_points_step2", "sort_features",
+             "transform_indexs", "find_neighbors_count", "find_neighbors_pack", "compute_pdf", "poisson_sampling",
+             "get_sampled_features", "spatial_conv"]
+    orig = {n: getattr(ops, n) for n in names}
+    events = []
+
+    def wrap(n):
+        def w(*a, **kw):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            r = orig[n](*a, **kw)
+            e.record()
+            events.append((n, s, e))
+            return r
+        return w
+
+    for n in names:
+        setattr(ops, n, wrap(n))
+    op_iters = min(args.steps, 10)
+    for i in range(op_iters):
+        flush_l2(flush)
+        eager.run_async(*resident[i % n_batches])
+    torch.cuda.synchronize(dev)
+    for n in names:
+        setattr(ops, n, orig[n])
+    per_call = {}
+    counters = {}
+    for idx, (n, s, e) in enumerate(events):
+        c = counters.get((n, idx // (len(events) // op_iters)), 0)
+        counters[(n, idx // (len(events) // op_iters))] = c + 1
+        per_call.setdefault((n, c), []).append(s.elapsed_time(e) * 1e3)
+    kernels = []
+    for (n, c), v in per_call.items():
+        opname = "sort_points" if n == "build_grid" else n
+        by = algorithmic_bytes(opname, c, sizes, B, k)
+        us = float(np.mean(v))
+        kernels.append({"op": n, "call": c, "us": round(us, 2), "alg_bytes": int(by),
+                        "gbs": round(by / us * 1e-3, 2) if us > 0 else None})
+    kernels.sort(key=lambda d: -d["us"])
+    peak, peak_src = measured_peak_gbs()
+    top = kernels[0]
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "top_kernel_traffic.json")
+    if os.path.exists(prof):
+        try:
+            with open(prof) as f:
+                traffic = json.load(f).get(top["op"] + ":" + str(top["call"]))
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "%s (call %d of the forward)" % (top["op"], top["call"]),
+                "achieved": top["gbs"], "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                "frac": round(top["gbs"] / peak, 5) if top["gbs"] else None, "traffic": traffic,
+                "alg_bytes_per_launch": top["alg_bytes"], "us_per_launch": top["us"],
+                "note": "whole step is latency-bound: working set ~10 MB << L2; per-op table in 'kernels'"}
+
+    # ---- e2e: host buffers, H2D + forward + D2H inside the timed call
+    hf = HostForward(eng, dev)
+    for i in range(3):
+        hf(*pinned[i % n_batches])
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        res = hf(*pinned[i % n_batches])
+        if world > 1:
+            gather_logits(res.to(dev, non_blocking=True), B * world, world)
+            torch.cuda.synchronize(dev)
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    h2d, d2h = hf.bytes_per_call(*pinned[0], B, NUM_CAT)
+
+    line = None
+    if rank == 0:
+        cpu = cpu_baseline(store, host[0], B, k) if world == 1 else None  # reported at N = 1 only
+        line = {
+            "metric": "MC-conv fwd points/sec (MCClassS, 1024 pts, batch 32 per GPU)", "value": round(value, 1),
+            "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": round(ms_per_step, 5), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic sphere-surface clouds (seeded), random-init weights",
+            "config": {"workload": "MCClassS forward (models/MCClassS.py), %d clouds x %d points per GPU, k=%d, "
+                                   "%d classes, 1 input feature" % (B, P, k, NUM_CAT),
+                       "parallelism": "dp%d (clouds sharded, one all_gather of logits)" % world,
+                       "l2": "flushed between timed steps (192 MiB write, outside the event pairs)",
+                       "levels": [sizes["N0"], sizes["M1"], sizes["M2"], sizes["M3"]],
+                       "pairs": [sizes["K1"], sizes["K2"], sizes["K3"]]},
+            "clocks": clocks,
+            "e2e": {"value": round(B * P * world / e2e_s, 1), "unit": "points/s", "ms_per_step": round(e2e_s * 1e3, 5),
+                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": launches_per_forward * args.steps,
+            "gpu_launches_per_step": launches_per_forward,
+            "wall_s_timed_region": round(t_wall, 4),
+            "plan_overflows": overflowed,
+            "roofline": roofline,
+            "kernels": kernels[:12],
+            "cpu_baseline": cpu,
+        }
+    return line
+
+
+def cpu_baseline(store, host_batch, B, k):
+    """Oracle port (oracle/mccnn_oracle.c + NumPy glue) of the same forward on the host, single thread, repeated for
+    >= ~10 s; plus the NumPy re-execution of config 1's spatial_conv that BASELINE.json names."""
+    from oracle import pipeline as OP, cpu as O, numpy_ops as NP
+    params = {n: v.detach().cpu().numpy() for n, v in store.vars.items()}
+    pts, bids, feats = host_batch
+    t0 = time.perf_counter()
+    reps = 0
+    while True:
+        OP.mcclasss_forward(pts, bids, feats, 1, B, k, NUM_CAT, params)
+        reps += 1
+        el = time.perf_counter() - t0
+        if el > 10.0 or reps >= 20:
+            break
+    fwd_s = el / reps
+    # config 1: single spatial_conv, 1 cloud x 1024 points, 3 -> 8 features, r = 0.1
+    p1, b1, f1 = make_batch(1, 1024, "sphere", seed=0, num_features=3)
+    mn, mx = O.compute_aabb(p1, b1, 1, True)
+    keys, idx = O.sort_points_step1(p1, b1, mn, mx, 1, 0.1, True)
+    sp, sb, sf, cells = O.sort_points_step2(p1, b1, f1, keys, idx, mn, mx, 1, 0.1, True)
+    start, pairs = O.find_neighbors(sp, sb, sp, cells, mn, mx, 0.1, 1, True)
+    pdf = O.compute_pdf(sp, sb, mn, mx, start, pairs, 0.2, 0.1, 1, True)
+    w = make_conv_weights(3, 8, True, seed=0)
+    best = 1e9
+    for _ in range(10):
+        t1 = time.perf_counter()
+        NP.spatial_conv(sp, sf, sb, pdf, sp, start, pairs, mn, mx, *w, 8, True, 1, 0.1, True, True)
+        best = min(best, time.perf_counter() - t1)
+    return {"value": round(pts.shape[0] / fwd_s, 1), "unit": "points/s", "cores": 1, "kind": "port",
+            "sample": "full workload batch (%d clouds x %d points), %d repetitions, %.2f s per forward, "
+                      "single-threaded C oracle + NumPy dense glue" % (B, pts.shape[0] // B, reps, fwd_s),
+            "host_cores_available": os.cpu_count(),
+            "numpy_spatial_conv_config1": {"ms": round(best * 1e3, 3), "pairs": int(pairs.shape[0]),
+                                           "points_per_s": round(1024 / best, 1), "numpy_threads": "BLAS default",
+                                           "note": "1 cloud x 1024 pts, 3->8 features, r=0.1, best of 10"}}
+
+
+# ----------------------------------------------------------------------------------------------- reference arm
+def run_reference(args, rank, world, dev):
+    """The reference's own CUDA kernels through the MCClassS op sequence (rank 0 only)."""
+    if rank != 0:
+        return None
+    from oracle import ref as R
+    if not R.available():
+        return {"impl": "reference", "unavailable": "oracle/_ref/libmccnn_ref.so not built (needs /root/reference)"}
+    from oracle import ref_pipeline as RP
+    from mccnn_b200 import variables  # parameter initialisation only (same seed => same weights as our arm)
+    from mccnn_b200.models import MCClassS
+    B, P, k = args.batch, args.points, args.k
+    store = variables.VariableStore(device=dev, seed=0)
+    n_batches = 4
+    host = [make_batch(B, P, "sphere", seed=i) for i in range(n_batches)]
+    pinned = [tuple(torch.from_numpy(a).pin_memory() for a in h) for h in host]
+    resident = [tuple(t.to(dev) for t in h) for h in pinned]
+    # create the variables with our builder once (names/shapes == the reference's), then hand them over as a dict
+    MCClassS.create_network(*resident[0], 1, B, k, NUM_CAT, False, 1.0, 1.0, store=store)
+    params = dict(store.vars)
+
+    def fwd(batch):
+        return RP.mcclasss_forward(batch[0], batch[1], batch[2], 1, B, k, NUM_CAT, params)
+
+    steps, warm = args.steps, max(args.warmup, 3)
+    for i in range(warm):
+        fwd(resident[i % n_batches])
+    torch.cuda.synchronize(dev)
+    flush = torch.zeros(192 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+    sampler = ClockSampler(dev.index)
+    sampler.start()
+    ms = []
+    for i in range(steps):
+        flush_l2(flush)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fwd(resident[i % n_batches])
+        e.record()
+        torch.cuda.synchronize(dev)
+        ms.append(s.elapsed_time(e))
+    clocks = sampler.stop()
+    ms_per_step = float(np.mean(ms))
+    # e2e: host buffers in, logits out
+    dev_in = tuple(torch.empty_like(t, device=dev) for t in pinned[0])
+    out_host = torch.empty((B, NUM_CAT), dtype=torch.float32).pin_memory()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        for d, h in zip(dev_in, pinned[i % n_batches]):
+            d.copy_(h, non_blocking=True)
+        out_host.copy_(fwd(dev_in)[:B])
+        torch.cuda.synchronize(dev)
+    e2e_s = (time.perf_counter() - t0) / steps
+    value = B * P / (ms_per_step * 1e-3)
+    h2d = sum(t.numel() * t.element_size() for t in pinned[0])
+    return {"impl": "reference",
+            "metric": "MC-conv fwd points/sec (MCClassS, 1024 pts, batch 32 per GPU)", "value": round(value, 1),
+            "unit": "points/s", "n_gpus": 1, "steps": steps, "warmup": warm, "ms_per_step": round(ms_per_step, 4),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic sphere-surface clouds (seeded), random-init weights",
+            "config": {"workload": "MCClassS forward, %d clouds x %d points, k=%d, %d classes" % (B, P, k, NUM_CAT),
+                       "path": "reference tf_ops CUDA kernels (unmodified, sm_100a) + TF-glue choreography shim"},
+            "clocks": clocks,
+            "e2e": {"value": round(B * P / e2e_s, 1), "unit": "points/s", "ms_per_step": round(e2e_s * 1e3, 4),
+                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": B * NUM_CAT * 4},
+            "cpu_baseline": {"value": round(value, 1), "unit": "points/s", "cores": 1, "kind": "reference",
+                             "sample": "full workload batch per step; the reference has NO CPU implementation of this "
+                                       "path -- this is its own CUDA path on the same GPU, driven by 1 host thread"}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--points", type=int, default=1024)
+    ap.add_argument("--k", type=int, default=64)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+
+    if args.impl == "reference":
+        if args.steps > 20:
+            args.steps = 20  # each reference step is ~100+ ms of launch-bound work
+        line = run_reference(args, rank, world, dev)
+        if line is not None:
+            print(json.dumps(line))
+        return
+
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    line = run_ours(args, rank, world, dev)
+    if rank == 0 and line is not None:
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

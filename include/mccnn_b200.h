@@ -30,6 +30,8 @@ int mc_abi_version(void);
 /* BLOCK_MLP_SIZE of the build == python get_block_size() (tf_ops/genCompileScript.py:20,46-47) */
 int mc_get_block_size(void);
 int mc_device_info(int* hostSmCount, int* hostCcMajor, int* hostCcMinor);
+/* kernels launched by this library so far in the process (diagnostics; bench.py reports it as gpu_launches) */
+long long mc_launch_count(void);
 
 /* computeAABB -- tf_ops/aabb_gpu.cc:38-40, tf_ops/aabb_gpu.cu:121-141.  workspace: 1 int. */
 int mc_compute_aabb(int scaleInv, int numPoints, int batchSize, const float* pts, const int* batchIds,
@@ -52,6 +54,17 @@ int mc_sort_points_step2(int numPoints, const int* dNumPoints, int batchSize, in
                          const float* pts, const int* batchIds, const float* features, const int* keys,
                          const int* newIdx, int* workspace, float* outPts, int* outBatchIds, float* outFeatures,
                          int* outCellIdx, void* stream);
+
+/* sortPointsStep1GPUKernel + sortPointsStep2GPUKernel fused into one launch -- tf_ops/sort_gpu.cu:436-497 -- for
+ * cloud-contiguous packed batches (utils/DataSet.py:816-818) and grids of at most 8192 cells per cloud.  Outputs are
+ * exactly those of the two calls above.  Contiguity is verified on the device: *dViolation (required, caller-zeroed)
+ * is set otherwise and the outputs are then unspecified.  workspace must be 8-byte aligned. */
+int mc_build_grid_supported(int batchSize, int numCells);
+long long mc_build_grid_workspace_ints(int numPoints);
+int mc_build_grid(int numPoints, const int* dNumPoints, int batchSize, int numFeatures, int numCells,
+                  const float* aabbMin, const float* aabbMax, const float* pts, const int* batchIds,
+                  const float* features, int* workspace, int* dViolation, int* keys, int* newIdx, float* outPts,
+                  int* outBatchIds, float* outFeatures, int* outCellIdx, void* stream);
 
 /* sortFeaturesBackGrad (python sort_features) -- tf_ops/sort_gpu.cc:165-170, tf_ops/sort_gpu.cu:529-540 */
 int mc_sort_features(int numPoints, const int* dNumPoints, int numFeatures, const float* in, const int* newIdx,

@@ -16,7 +16,7 @@ import torch
 
 from .MCConvModule import (compute_aabb, sort_points_step1, sort_points_step2, sort_features, sort_features_back,
                            compute_pdf, poisson_sampling, get_sampled_features, spatial_conv, get_block_size,
-                           transform_indexs, find_neighbors)
+                           transform_indexs, find_neighbors, sort_points)
 from . import runtime as _rt
 from . import variables as _vars
 
@@ -53,11 +53,10 @@ class PointHierarchy:
         currPts, currFeatures, currBatchIds = inPoints, inFeatures, inBatchIds
         for level, currRadius in enumerate(radiusList):
             _log("Level: " + str(level + 1) + " | Poisson Disk Radius: " + str(currRadius))
-            keys, indexs = sort_points_step1(currPts, currBatchIds, self.aabbMin_, self.aabbMax_, self.batchSize_,
-                                             currRadius, self.relativeRadius_)
-            sortPts, sortBatchs, sortFeatures, cellIndexs = sort_points_step2(
-                currPts, currBatchIds, currFeatures, keys, indexs, self.aabbMin_, self.aabbMax_, self.batchSize_,
-                currRadius, self.relativeRadius_)
+            # sort_points_step1 + sort_points_step2 (utils/MCConvBuilder.py:106-110), fused into one launch
+            keys, indexs, sortPts, sortBatchs, sortFeatures, cellIndexs = sort_points(
+                currPts, currBatchIds, currFeatures, self.aabbMin_, self.aabbMax_, self.batchSize_, currRadius,
+                self.relativeRadius_)
             sampledPts, sampledBatchsIds, sampledIndexs = poisson_sampling(
                 sortPts, sortBatchs, cellIndexs, aabbMin, aabbMax, currRadius, batchSize, self.relativeRadius_)
             sampledFeatures = get_sampled_features(sampledIndexs, sortFeatures)
@@ -131,11 +130,10 @@ class ConvolutionBuilder:
             currGridTuple = self.cacheGrids_[keyGrid]
             sortFeatures = sort_features(inFeatures, currGridTuple[3])
         else:
-            keys, indexs = sort_points_step1(ph.points_[inPointLevel], ph.batchIds_[inPointLevel], ph.aabbMin_,
-                                             ph.aabbMax_, ph.batchSize_, convRadius, currRelativeRadius)
-            sortPts, sortBatchs, sortFeatures, cellIndexs = sort_points_step2(
-                ph.points_[inPointLevel], ph.batchIds_[inPointLevel], inFeatures, keys, indexs, ph.aabbMin_,
-                ph.aabbMax_, ph.batchSize_, convRadius, currRelativeRadius)
+            # sort_points_step1 + sort_points_step2 (utils/MCConvBuilder.py:353-361), fused into one launch
+            keys, indexs, sortPts, sortBatchs, sortFeatures, cellIndexs = sort_points(
+                ph.points_[inPointLevel], ph.batchIds_[inPointLevel], inFeatures, ph.aabbMin_, ph.aabbMax_,
+                ph.batchSize_, convRadius, currRelativeRadius)
             currGridTuple = (sortPts, sortBatchs, cellIndexs, indexs)
             self.cacheGrids_[keyGrid] = currGridTuple
 

@@ -20,7 +20,7 @@ from .runtime import count_of as _cnt, tag as _tag
 
 __all__ = ["compute_aabb", "sort_points_step1", "sort_points_step2", "sort_features", "sort_features_back",
            "transform_indexs", "find_neighbors", "compute_pdf", "poisson_sampling", "get_sampled_features",
-           "spatial_conv", "get_block_size"]
+           "spatial_conv", "get_block_size", "sort_points"]
 
 
 def _req(cond, msg):
@@ -85,6 +85,43 @@ def sort_points_step2(inPts, inBatchIds, inFeatures, keys, indexs, aabbMin, aabb
     nd = _cnt(inPts)
     p, b, f, cells = ops.sort_points_step2(inPts, inBatchIds.reshape(-1), inFeatures, keys, indexs, batchSize, n, nd)
     return _tag(p, nd), _tag(b.reshape(-1, 1), nd), _tag(f, nd), cells
+
+
+def sort_points(inPts, inBatchIds, inFeatures, aabbMin, aabbMax, batchSize, cellSize, scaleInv):
+    """sort_points_step1 followed by sort_points_step2 (the only way the reference ever uses them,
+    utils/MCConvBuilder.py:106-110,353-361) -> (keys, indexs, sortPts, sortBatchIds, sortFeatures, cellIndexs).
+
+    Not part of the reference API: an extension that lets the builder issue the whole grid sort as ONE kernel launch
+    (csrc/grid_build.cu) when the batch is cloud-contiguous and the grid has <= 8192 cells per cloud.  Results are
+    identical to the two-step ops.  Contiguity is verified on the device; in exact / record mode a violation falls
+    back to the two-step path here, in planned mode it raises the plan's overflow flag (the engine then re-records)."""
+    _req(batchSize > 0, "SortPoints expects a positive batch size")
+    _req(inPts.dim() == 2 and inPts.shape[1] == 3, "SortPoints expects points with three components")
+    N = inPts.shape[0]
+    _check_bids(inBatchIds, N, "SortPoints")
+    _req(inFeatures.dim() == 2 and inFeatures.shape[0] == N, "SortPoints expects features of shape (numPoints, C)")
+    _check_aabb(aabbMin, aabbMax, batchSize, "SortPoints")
+    n = _num_cells(aabbMin, aabbMax, cellSize, scaleInv)
+    nd = _cnt(inPts)
+    mode = _rt.mode()
+    fused = ops.build_grid_supported(batchSize, n) and N > 0
+    if fused and mode == "planned":
+        plan = _rt.current_plan()
+        fused = plan.next_flag()
+        violation = plan.overflow
+    elif fused:
+        violation = torch.zeros((1,), dtype=torch.int32, device=inPts.device)
+    if fused:
+        keys, idx, p, b, f, cells = ops.build_grid(inPts, inBatchIds.reshape(-1), inFeatures, aabbMin, aabbMax,
+                                                   batchSize, n, violation, nd)
+        if mode != "planned":
+            fused = int(violation.item()) == 0
+            if mode == "record":
+                _rt.current_plan().flags.append(fused)
+    if not fused:
+        keys, idx = ops.sort_points_step1(inPts, inBatchIds.reshape(-1), aabbMin, aabbMax, batchSize, n, nd)
+        p, b, f, cells = ops.sort_points_step2(inPts, inBatchIds.reshape(-1), inFeatures, keys, idx, batchSize, n, nd)
+    return _tag(keys, nd), _tag(idx, nd), _tag(p, nd), _tag(b.reshape(-1, 1), nd), _tag(f, nd), cells
 
 
 def sort_features(inFeatures, indexs):

@@ -22,12 +22,16 @@ SIGNATURES = {
     "mc_abi_version": (_c_int, []),
     "mc_get_block_size": (_c_int, []),
     "mc_device_info": (_c_int, [_ptr, _ptr, _ptr]),
+    "mc_launch_count": (_c_ll, []),
     "mc_compute_aabb": (_c_int, [_c_int, _c_int, _c_int, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr]),
     "mc_determine_num_cells": (_c_int, [_c_int, _c_float, _ptr, _ptr, _ptr, _ptr, _ptr]),
     "mc_sort_step1_workspace_ints": (_c_ll, [_c_int, _c_int, _c_int]),
     "mc_sort_points_step1": (_c_int, [_c_int, _ptr, _c_int, _c_int, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr]),
     "mc_sort_points_step2": (_c_int, [_c_int, _ptr, _c_int, _c_int, _c_int, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr,
                                       _ptr, _ptr, _ptr, _ptr]),
+    "mc_build_grid_supported": (_c_int, [_c_int, _c_int]),
+    "mc_build_grid_workspace_ints": (_c_ll, [_c_int]),
+    "mc_build_grid": (_c_int, [_c_int, _ptr, _c_int, _c_int, _c_int] + [_ptr] * 14),
     "mc_sort_features": (_c_int, [_c_int, _ptr, _c_int, _ptr, _ptr, _ptr, _ptr]),
     "mc_sort_features_back": (_c_int, [_c_int, _ptr, _c_int, _ptr, _ptr, _ptr, _ptr]),
     "mc_transform_indexs": (_c_int, [_c_int, _ptr, _c_int, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr]),

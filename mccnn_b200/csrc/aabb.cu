@@ -116,5 +116,6 @@ extern "C" int mc_compute_aabb(int scaleInv, int numPoints, int batchSize, const
     int grid = mc::cdiv(numPoints > 0 ? numPoints : 1, 256);
     if (grid > 148 * 8) grid = 148 * 8;
     mc::aabb_reduce_kernel<<<grid, 256, 0, s>>>(scaleInv != 0, numPoints, batchSize, pts, batchIds, mnK, mxK, workspace);
+    mc::count_launches(1);
     return mc::check_launch("mc_compute_aabb");
 }

@@ -4,6 +4,7 @@
 // reports shape errors through TensorFlow's OP_REQUIRES.  Here every entry point returns an int status (0 = ok,
 // 1 = invalid argument, 2 = CUDA error) and mc_last_error() returns the message of the calling thread's last
 // failure; the Python layer turns them into ValueError / RuntimeError.
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 
@@ -20,7 +21,12 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+static std::atomic<long long> g_kernelLaunches{0};
+
+void count_launches(int n) { g_kernelLaunches.fetch_add(n, std::memory_order_relaxed); }
+
 int check_launch(const char* what) {
+    count_launches(1);  // entry points launching more than one kernel add the rest with count_launches()
     cudaError_t e = cudaPeekAtLastError();
     if (e == cudaSuccess) return 0;
     cudaGetLastError();  // clear the sticky launch error so that later calls are not blamed for it
@@ -36,6 +42,9 @@ extern "C" const char* mc_last_error(void) { return mc::g_lastError; }
 extern "C" int mc_get_block_size(void) { return MC_BLOCK_MLP; }
 
 extern "C" int mc_abi_version(void) { return 1; }
+
+// number of kernels this library has launched so far in the process (bench.py reports it as gpu_launches)
+extern "C" long long mc_launch_count(void) { return mc::g_kernelLaunches.load(); }
 
 // SM count / compute capability of the current device; lets the host refuse to run on anything but sm_100.
 extern "C" int mc_device_info(int* smCount, int* ccMajor, int* ccMinor) {

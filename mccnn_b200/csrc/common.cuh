@@ -98,7 +98,8 @@ __device__ __constant__ const signed char kOffsPool[27][3] = {
 // ---- host side -------------------------------------------------------------------------------
 namespace mc {
 void set_error(const char* fmt, ...);
-int check_launch(const char* what);  // cudaPeekAtLastError -> status + message
+int check_launch(const char* what);  // cudaPeekAtLastError -> status + message; counts one kernel launch
+void count_launches(int n);          // additional kernel launches of the calling entry point
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 }  // namespace mc
 

@@ -214,6 +214,7 @@ extern "C" int mc_sort_points_step1(int numPoints, const int* dNumPoints, int ba
     launch_scan(counters, nullptr, G, tileSums, nullptr, s);
     scatter_perm_kernel<<<grid, kPtThreads, 0, s>>>(dNumPoints, numPoints, keys, arrival, counters, tileSums, perm);
     stable_rank_kernel<<<grid, kPtThreads, 0, s>>>(dNumPoints, numPoints, G, keys, counters, tileSums, perm, newIdx);
+    count_launches(4);
     return check_launch("mc_sort_points_step1");
 }
 
@@ -232,6 +233,7 @@ extern "C" int mc_sort_points_step2(int numPoints, const int* dNumPoints, int ba
                                                    outBatchIds, workspace);
     launch_permute_rows<true>(dNumPoints, numPoints, numFeatures, features, newIdx, outFeatures, s);
     cell_table_kernel<<<grid, kPtThreads, 0, s>>>(dNumPoints, numPoints, workspace, outCellIdx);
+    count_launches(numFeatures > 0 ? 2 : 1);
     return check_launch("mc_sort_points_step2");
 }
 
@@ -266,5 +268,6 @@ extern "C" int mc_transform_indexs(int numIndexs, const int* dNumIndexs, int num
     if (numIndexs > 0)
         gather_index_kernel<<<cdiv(numIndexs, kPtThreads), kPtThreads, 0, s>>>(dNumIndexs, numIndexs, inIndexs,
                                                                              workspace, out);
+    count_launches(1);
     return check_launch("mc_transform_indexs");
 }

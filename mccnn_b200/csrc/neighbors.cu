@@ -98,6 +98,7 @@ extern "C" int mc_find_neighbors_count(int scaleInv, int numSamples, const int* 
             scaleInv != 0, dNumSamples, numSamples, numCells, radius, samples, sampleBatchIds, pts2,
             reinterpret_cast<const int2*>(cellIdx), aabbMin, aabbMax, startIdx, nullptr, nullptr, 0, nullptr);
     launch_scan(startIdx, dNumSamples, numSamples, workspace, dNumNeighbors, s);
+    count_launches(2);
     return check_launch("mc_find_neighbors_count");
 }
 

@@ -251,6 +251,7 @@ extern "C" int mc_spatial_conv(int avg, int scaleInv, int numNeighbors, const in
         long long total = (long long)numSamples * numOutFeatures;
         combine_kernel<<<cdiv(total, 256), 256, 0, s>>>(dNumSamples, numSamples, C, numOutFeatures, nb * 8, workspace,
                                                         outFeatures);
+        count_launches(1);
     }
     return check_launch("mc_spatial_conv");
 }

@@ -92,6 +92,56 @@ class PlannedForward:
             out = self._record(pts, bids, feats)
         return out
 
+    def calibrate(self, batches):
+        """Record several representative batches (same shapes) and plan for the element-wise maximum of their sizes."""
+        sizes, flags = None, None
+        for pts, bids, feats in batches:
+            self._record(pts, bids, feats)
+            s, f = self.plan.sizes, self.plan.flags
+            sizes = list(s) if sizes is None else [max(a, b) for a, b in zip(sizes, s)]
+            flags = list(f) if flags is None else [a and b for a, b in zip(flags, f)]
+        self.plan.sizes, self.plan.flags = sizes, flags
+        self.plan.finalize()
+        self.graph = None
+        return self.plan
+
+
+class HostForward:
+    """End-to-end call for host-resident batches: pinned host buffers -> H2D -> planned forward -> D2H of the result
+    (and of the overflow flag) -> host tensor.  This is the user-facing equivalent of the reference's
+    `sess.run(logits, feed_dict)` (ModelNet/ModelNetEval.py:123-125)."""
+
+    def __init__(self, engine, device):
+        self.engine = engine
+        self.device = torch.device(device)
+        self._dev = None
+        self._out_host = None
+        self._flag_host = torch.zeros((1,), dtype=torch.int32).pin_memory()
+
+    def __call__(self, pts_host, bids_host, feats_host):
+        """Arguments: CPU tensors (ideally pinned).  Returns a pinned CPU tensor [out_rows, F] (reused across calls)."""
+        if self._dev is None or tuple(self._dev[0].shape) != tuple(pts_host.shape) or \
+                tuple(self._dev[2].shape) != tuple(feats_host.shape):
+            self._dev = tuple(torch.empty(t.shape, dtype=t.dtype, device=self.device)
+                              for t in (pts_host, bids_host, feats_host))
+        for d, h in zip(self._dev, (pts_host, bids_host, feats_host)):
+            d.copy_(h, non_blocking=True)
+        out, flag = self.engine.run_async(*self._dev)
+        if self._out_host is None or tuple(self._out_host.shape) != tuple(out.shape):
+            self._out_host = torch.empty(out.shape, dtype=out.dtype).pin_memory()
+        self._out_host.copy_(out, non_blocking=True)
+        self._flag_host.copy_(flag, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        if int(self._flag_host[0]) != 0:  # a planned capacity was exceeded: exact re-run, re-plan
+            self.engine.stats["overflows"] += 1
+            self._out_host.copy_(self.engine._record(*self._dev))
+        return self._out_host
+
+    def bytes_per_call(self, pts_host, bids_host, feats_host, out_rows, out_cols):
+        h2d = sum(t.numel() * t.element_size() for t in (pts_host, bids_host, feats_host))
+        d2h = out_rows * out_cols * 4 + 4
+        return h2d, d2h
+
 
 # ---- data-parallel sharding (one process per GPU) ---------------------------------------------------------------
 

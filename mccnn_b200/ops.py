@@ -98,6 +98,29 @@ def sort_points_step2(pts, bids, feats, keys, new_idx, batch_size, n_cells, n_de
     return out_pts, out_bids, out_feats, cell_idx
 
 
+def build_grid_supported(batch_size, n_cells):
+    return bool(lib.mc_build_grid_supported(batch_size, n_cells))
+
+
+def build_grid(pts, bids, feats, aabb_min, aabb_max, batch_size, n_cells, violation, n_dev=None):
+    """Fused step1 + step2 for cloud-contiguous batches (one launch).  `violation` (int32[1], device) is set when the
+    batch is not contiguous.  Returns (keys, new_idx, sort_pts, sort_bids, sort_feats, cell_idx)."""
+    pts, bids, feats = _f(pts), _i(bids), _f(feats)
+    dev = _dev(pts)
+    N, C = pts.shape[0], feats.shape[1]
+    keys = torch.empty((N,), dtype=_i32, device=dev)
+    new_idx = torch.empty((N,), dtype=_i32, device=dev)
+    out_pts = torch.empty_like(pts)
+    out_bids = torch.empty_like(bids)
+    out_feats = torch.empty_like(feats)
+    cell_idx = torch.empty((batch_size, n_cells, n_cells, n_cells, 2), dtype=_i32, device=dev)
+    ws = torch.empty((lib.mc_build_grid_workspace_ints(N),), dtype=_i32, device=dev)
+    check(lib.mc_build_grid(N, _p(n_dev), batch_size, C, n_cells, _p(aabb_min), _p(aabb_max), _p(pts), _p(bids),
+                            _p(feats), _p(ws), _p(violation), _p(keys), _p(new_idx), _p(out_pts), _p(out_bids),
+                            _p(out_feats), _p(cell_idx), _stream()))
+    return keys, new_idx, out_pts, out_bids, out_feats, cell_idx
+
+
 def sort_features(feats, new_idx, n_dev=None):
     feats, new_idx = _f(feats), _i(new_idx)
     out = torch.empty_like(feats)

@@ -22,6 +22,8 @@ class Plan:
     def __init__(self, slack=1.3, granule=256):
         self.sizes = []        # recorded live sizes in call order
         self.capacities = []   # planned capacities, same order
+        self.flags = []        # recorded boolean decisions in call order (e.g. "this batch is cloud-contiguous")
+        self._flag_cursor = 0
         self.slack = slack
         self.granule = granule
         self.overflow = None   # int32[1] device flag, set by kernels when a capacity is exceeded
@@ -34,8 +36,16 @@ class Plan:
 
     def begin(self, device):
         self._cursor = 0
+        self._flag_cursor = 0
         if self.overflow is None or self.overflow.device != device:
             self.overflow = torch.zeros((1,), dtype=torch.int32, device=device)
+
+    def next_flag(self):
+        if self._flag_cursor >= len(self.flags):
+            raise RuntimeError("mccnn_b200: the planned run takes more recorded decisions than were recorded")
+        f = self.flags[self._flag_cursor]
+        self._flag_cursor += 1
+        return f
 
     def next_capacity(self):
         if self._cursor >= len(self.capacities):

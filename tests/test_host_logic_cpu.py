@@ -1,0 +1,164 @@
+"""No-GPU tests of the host-side logic: execution plans, variable store / initialisers, batch sharding, and the
+world_size-2 gloo path of the one collective (all_gather of per-cloud logits)."""
+import math
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from common import make_batch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_plan_capacities_and_cursors():
+    from mccnn_b200 import runtime
+    with runtime.record(slack=1.25) as plan:
+        assert runtime.mode() == "record"
+        plan.sizes.extend([1000, 1, 300000])
+        plan.flags.extend([True, False])
+    assert runtime.mode() == "exact"
+    assert plan.capacities == [1280, 256, 375040]
+    assert all(c >= s for c, s in zip(plan.capacities, plan.sizes))
+    plan._cursor = plan._flag_cursor = 0
+    assert [plan.next_capacity() for _ in range(3)] == plan.capacities
+    assert [plan.next_flag(), plan.next_flag()] == [True, False]
+    with pytest.raises(RuntimeError):
+        plan.next_capacity()
+    with pytest.raises(RuntimeError):
+        plan.next_flag()
+    t = torch.zeros(4)
+    assert runtime.count_of(t) is None
+    c = torch.tensor([3], dtype=torch.int32)
+    assert runtime.count_of(runtime.tag(t, c)) is c
+
+
+def test_variable_store_initialisers_follow_tensorflow():
+    from mccnn_b200.variables import VariableStore
+    vs = VariableStore(device="cpu", seed=1)
+    w = vs.get_variable("w", [3, 64], "glorot")
+    lim = math.sqrt(3.0 / ((3 + 64) / 2.0))               # variance_scaling(1.0, FAN_AVG, uniform)
+    assert w.shape == (3, 64) and float(w.abs().max()) <= lim and float(w.abs().max()) > 0.8 * lim
+    w3 = vs.get_variable("w3", [16, 8, 8], "glorot")        # fan_in = fan_out = 8 * 16 (receptive field 16)
+    assert float(w3.abs().max()) <= math.sqrt(3.0 / 128.0)
+    assert float(vs.get_variable("b", [7], "zeros").abs().sum()) == 0.0
+    assert vs.get_variable("w", [3, 64]) is w               # reuse by name
+    with pytest.raises(ValueError):
+        vs.get_variable("w", [4, 64])
+    sd = vs.state_dict()
+    vs2 = VariableStore(device="cpu", seed=9)
+    vs2.load_state_dict(sd)
+    assert torch.equal(vs2.vars["w3"], w3)
+
+
+def test_shard_ranges_partition_the_batch():
+    from mccnn_b200.engine import shard_range, shard_batch
+    for B in (1, 7, 32, 33):
+        for W in (1, 2, 3, 8):
+            r = [shard_range(B, k, W) for k in range(W)]
+            assert r[0][0] == 0 and r[-1][1] == B
+            assert all(a[1] == b[0] for a, b in zip(r, r[1:]))
+            assert max(h - l for l, h in r) - min(h - l for l, h in r) <= 1
+    pts, bids, feats = make_batch(5, 100, "cube", seed=0, ragged=True)
+    got = []
+    for k in range(2):
+        p, b, f, nb, (lo, hi) = shard_batch(pts, bids, feats, 5, k, 2)
+        assert nb == hi - lo and b.min() == 0 and b.max() == nb - 1
+        assert np.array_equal(p, pts[(bids[:, 0] >= lo) & (bids[:, 0] < hi)])
+        got.append(p.shape[0])
+    assert sum(got) == pts.shape[0]
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _gloo_worker(rank, world, port, B, k, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    from mccnn_b200.engine import shard_batch, gather_logits
+    from oracle import pipeline as OP
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    pts, bids, feats = make_batch(B, 256, "sphere", seed=5)
+    params = _params(k)
+    p, b, f, nb, _ = shard_batch(pts, bids, feats, B, rank, world)
+    local, _ = OP.mcclasss_forward(p, b, f, 1, nb, k, 10, params)        # this rank's clouds only
+    full = gather_logits(torch.from_numpy(local), B, world)               # the single collective of the step
+    if rank == 0:
+        q.put(full.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _params(k, numCat=10, seed=0):
+    """MCClassS parameter dictionary (reference variable names) for the oracle pipeline."""
+    rng = np.random.default_rng(seed)
+    p = {}
+
+    def conv(name, nOut):
+        nb = (nOut + 7) // 8
+        p[name + "_weights"] = rng.uniform(-0.5, 0.5, (3, 8 * nb)).astype(np.float32)
+        p[name + "_biases"] = rng.uniform(-0.1, 0.1, (8 * nb,)).astype(np.float32)
+        for s in ("2", "3"):
+            p[name + "_weights" + s] = rng.uniform(-0.5, 0.5, (nb, 8, 8)).astype(np.float32)
+            p[name + "_biases" + s] = rng.uniform(-0.1, 0.1, (nb, 8)).astype(np.float32)
+
+    def bn(name, c):
+        p[name + "/gamma"] = rng.uniform(0.8, 1.2, (c,)).astype(np.float32)
+        p[name + "/beta"] = rng.uniform(-0.1, 0.1, (c,)).astype(np.float32)
+        p[name + "/moving_mean"] = rng.uniform(-0.1, 0.1, (c,)).astype(np.float32)
+        p[name + "/moving_variance"] = rng.uniform(0.8, 1.2, (c,)).astype(np.float32)
+
+    def dense(w, b, i, o):
+        p[w] = rng.uniform(-0.3, 0.3, (i, o)).astype(np.float32)
+        p[b] = rng.uniform(-0.1, 0.1, (o,)).astype(np.float32)
+
+    conv("Conv_1", k)
+    conv("Conv_2", 2 * k)
+    conv("Conv_3", 4 * k)
+    bn("Reduce_1_In_BN_BN", k)
+    dense("Reduce_1_weights", "Reduce_1_biases", k, 2 * k)
+    bn("Reduce_1_Out_BN_BN", 2 * k)
+    bn("Reduce_2_In_BN_BN", 2 * k)
+    dense("Reduce_2_weights", "Reduce_2_biases", 2 * k, 4 * k)
+    bn("Reduce_2_Out_BN_BN", 4 * k)
+    bn("BNRELUDROP_final_BN", 4 * k)
+    bn("Final_Logits_BN_Init", 4 * k)
+    dense("Final_Logits_weights1", "Final_Logits_biases1", 4 * k, 2 * k)
+    bn("Final_Logits_BN_h1", 2 * k)
+    dense("Final_Logits_weights2", "Final_Logits_biases2", 2 * k, k)
+    bn("Final_Logits_BN_h2", k)
+    dense("Final_Logits_weights3", "Final_Logits_biases3", k, numCat)
+    return p
+
+
+def test_sharded_forward_equals_unsharded_gloo_world2():
+    """Clouds are independent units: computing each rank's clouds separately and all_gathering
+    the logits reproduces the single-process result exactly.  Runs the real collective on the gloo backend."""
+    import torch.multiprocessing as mp
+    from oracle import pipeline as OP
+    B, k, world = 5, 8, 2
+    pts, bids, feats = make_batch(B, 256, "sphere", seed=5)
+    want, trace = OP.mcclasss_forward(pts, bids, feats, 1, B, k, 10, _params(k))
+    assert want.shape == (B, 10) and trace[0]["levels"][-1] == B
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, world, port, B, k, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got.shape == want.shape
+    assert np.array_equal(got, want)

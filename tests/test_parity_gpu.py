@@ -62,6 +62,11 @@ def test_aabb_sort_bit_exact(env, B, N, dist, ragged, radius, scaleInv):
     names = ["aabbMin", "aabbMax", "keys", "indexs", "sortPts", "sortBatchIds", "sortFeatures", "cellIndexs"]
     for name, a, b in zip(names, g, o):
         assert np.array_equal(e["A"](a).reshape(-1), np.asarray(b).reshape(-1)), name
+    # the fused one-launch grid build (builder path) gives the same six tensors
+    fk, fi, fp, fb, ff, fc = e["M"].sort_points(e["T"](pts), e["T"](bids), e["T"](feats), g[0], g[1], B, radius,
+                                                 scaleInv)
+    for name, a, b in zip(names[2:], (fk, fi, fp, fb, ff, fc), o[2:]):
+        assert np.array_equal(e["A"](a).reshape(-1), np.asarray(b).reshape(-1)), "fused " + name
     tail = pts.shape[0] % 256  # reference aabb leaves smem rows uninitialised when 0 < N % 256 < B (aabb_gpu.cu:69-78)
     if e["R"] is not None and (tail == 0 or tail >= B):
         R, T, A = e["R"], e["T"], e["A"]
@@ -229,6 +234,19 @@ def test_edge_cases(env):
     fb = np.zeros((1, 1), np.int32)
     gs, gp = M.find_neighbors(T(far), T(fb), T(sp), T(cells), T(mn), T(mx), 0.05, 1, True)
     assert gp.shape[0] == 0 and A(gs).tolist() == [[0]]
+    # a packed batch whose clouds are interleaved (not contiguous): the general path, and the fused path's device-side
+    # contiguity check falling back to it, both match the oracle
+    p2, b2, f2 = make_batch(3, 400, "cube", seed=9, num_features=2)
+    perm = np.random.default_rng(1).permutation(p2.shape[0])
+    p2, b2, f2 = p2[perm], b2[perm], f2[perm]
+    omn, omx = O.compute_aabb(p2, b2, 3, True)
+    gmn, gmx = M.compute_aabb(T(p2), T(b2), 3, True)
+    assert np.array_equal(A(gmn), omn) and np.array_equal(A(gmx), omx)
+    ok, oi = O.sort_points_step1(p2, b2, omn, omx, 3, 0.2, True)
+    osp, osb, osf, ocells = O.sort_points_step2(p2, b2, f2, ok, oi, omn, omx, 3, 0.2, True)
+    fused = M.sort_points(T(p2), T(b2), T(f2), gmn, gmx, 3, 0.2, True)
+    for a, b in zip(fused, (ok, oi, osp, osb, osf, ocells)):
+        assert np.array_equal(A(a).reshape(-1), np.asarray(b).reshape(-1))
     # invalid attributes raise like OP_REQUIRES
     with pytest.raises(ValueError):
         M.find_neighbors(T(far), T(fb), T(sp), T(cells), T(mn), T(mx), -1.0, 1, True)
