@@ -68,6 +68,35 @@ __device__ __forceinline__ bool within_radius(float px, float py, float pz, floa
     return __fsqrt_rn(d2) < r;
 }
 
+// The same predicate without the square root in the inner loop.  sqrt_rn is monotone, so
+// { d2 >= 0 : sqrt_rn(d2) < r } is a down-set with a largest element t*; exact_radius_threshold finds t* by walking
+// ulp by ulp from r*r (at most a few steps), after which   d2 <= t*  <=>  sqrt_rn(d2) < r   for EVERY float d2
+// (NaN compares false on both sides; r <= 0 gives t* = -1: no match).  Bit-exact replacement, ~10 SASS instructions
+// (MUFU.RSQ + Newton + fix-up) shorter per candidate.
+__device__ __forceinline__ float exact_radius_threshold(float r) {
+    if (!(r > 0.0f)) return -1.0f;
+    if (r > 1.8e19f) return FLT_MAX;  // r*r overflows: every finite d2 qualifies
+    float t = __fmul_rn(r, r);
+    if (__fsqrt_rn(t) < r) {
+        while (true) {
+            float up = __int_as_float(__float_as_int(t) + 1);
+            if (!(__fsqrt_rn(up) < r)) break;
+            t = up;
+        }
+    } else {
+        while (!(__fsqrt_rn(t) < r)) {
+            if (t == 0.0f) return -1.0f;
+            t = __int_as_float(__float_as_int(t) - 1);
+        }
+    }
+    return t;
+}
+
+__device__ __forceinline__ float dist2_ref(float px, float py, float pz, float qx, float qy, float qz) {
+    float dx = __fsub_rn(qx, px), dy = __fsub_rn(qy, py), dz = __fsub_rn(qz, pz);
+    return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+}
+
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
 __device__ __forceinline__ int warp_inclusive_scan(int v) {

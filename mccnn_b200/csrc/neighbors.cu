@@ -32,6 +32,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32)
     const float sx = samples[(size_t)i * 3], sy = samples[(size_t)i * 3 + 1], sz = samples[(size_t)i * 3 + 2];
     int cx, cy, cz;
     cell_of(f, sx, sy, sz, n, cx, cy, cz);
+    const float thr = exact_radius_threshold(f.radius);  // d2 <= thr  <=>  sqrt(d2) < radius, exactly
 
     // lanes 0..26: (lo,hi) of neighbour cell `lane`
     int lo = 0, hi = 0;
@@ -60,8 +61,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32)
             int j = j0 + lane;
             bool in = false;
             if (j < chi)
-                in = within_radius(sx, sy, sz, pts2[(size_t)j * 3], pts2[(size_t)j * 3 + 1], pts2[(size_t)j * 3 + 2],
-                                   f.radius);
+                in = dist2_ref(sx, sy, sz, pts2[(size_t)j * 3], pts2[(size_t)j * 3 + 1], pts2[(size_t)j * 3 + 2]) <= thr;
             unsigned hit = __ballot_sync(MC_FULL_MASK, in);
             if (FILL && in) {
                 int slot = base + count + __popc(hit & ltMask);

@@ -5,18 +5,21 @@
 // cell walking its 27 neighbour cells serially -- then blocks the host on the sample count.  Here the whole op is ONE
 // kernel launch (plus one memset):
 //   * one CTA per cloud (clouds claimed through a ticket so that CTA order == cloud order); the 27 colour phases run
-//     inside the kernel separated by __syncthreads(); the accepted flags of the cloud live in shared memory;
-//   * a WARP owns a cell of the phase.  It first compacts the already-accepted points of the 26 neighbour cells into
-//     a small shared-memory list (lanes = neighbour cells), then tests its own points against that list with one
-//     point per lane, and finally resolves the order dependence INSIDE the cell (a point is rejected by an earlier
-//     accepted point of the same cell) with a short shuffle loop -- so the serial chain is the cell population, not
-//     the 27-cell neighbourhood population x memory latency;
+//     inside the kernel separated by __syncthreads(); the accepted flags of the cloud live in shared memory, and
+//     the non-empty cells of every phase are listed once up front so that no warp ever visits an empty cell;
+//   * a WARP owns a cell of the phase.  It (A) compacts the already-accepted points of the 26 neighbour cells into a
+//     small shared-memory list (lanes = neighbour cells), (B) tests its own points against that list with the 32
+//     lanes spread over (point, list slice) pairs, and (C) resolves the order dependence INSIDE the cell -- a point
+//     is rejected by an earlier accepted point of the same cell -- by walking only the still-unblocked points with
+//     shuffles.  The serial chain is therefore the number of unblocked points of a cell (typically 1-3), not the
+//     27-cell neighbourhood population x memory latency;
+//   * distances use the square-root-free exact predicate (common.cuh exact_radius_threshold);
 //   * the accepted set is identical to the reference's (deterministic there too: same-phase cells are >= 3 cells
 //     apart and a thread only flags points of its own cell);
 //   * output order: the reference's is atomic-arrival order inside a (cloud, phase) launch; the canonical order
 //     (cloud, phase, ascending position in the sorted array) is produced in-kernel by a stable per-phase
-//     compaction, and clouds are concatenated through a chained prefix (each CTA waits for its predecessor's
-//     running total only after all of its own work is done).  The sample count stays on the device.
+//     compaction, and clouds are concatenated through a decoupled look-back prefix (lookback.cuh).  The sample
+//     count stays on the device.
 #include "common.cuh"
 #include "lookback.cuh"
 
@@ -28,6 +31,15 @@ constexpr int kSelWarps = kSelThreads / 32;
 constexpr int kSelFlagBytes = 48 * 1024;  // per-cloud accepted flags kept in shared memory up to this many points
 constexpr int kListCap = 128;             // accepted neighbour candidates a warp keeps in shared memory
 constexpr int kSelfOffset = 17;           // index of (0,0,0) in kOffsPool
+constexpr int kCellListCap = 8192;        // cells per cloud up to which the per-phase non-empty cell lists are built
+
+// phase (index into kOffsPool) of the offset (ox, oy, oz), indexed by (ox+1)*9 + (oy+1)*3 + (oz+1)
+__device__ __constant__ const unsigned char kPhaseOfOffset[27] = {
+    /*(-1,-1,-1)*/ 25, /*(-1,-1,0)*/ 15, /*(-1,-1,1)*/ 26, /*(-1,0,-1)*/ 24, /*(-1,0,0)*/ 12, /*(-1,0,1)*/ 22,
+    /*(-1,1,-1)*/ 6,   /*(-1,1,0)*/ 16,  /*(-1,1,1)*/ 11,  /*(0,-1,-1)*/ 7,  /*(0,-1,0)*/ 5,  /*(0,-1,1)*/ 1,
+    /*(0,0,-1)*/ 18,   /*(0,0,0)*/ 17,   /*(0,0,1)*/ 4,    /*(0,1,-1)*/ 14,  /*(0,1,0)*/ 3,   /*(0,1,1)*/ 2,
+    /*(1,-1,-1)*/ 13,  /*(1,-1,0)*/ 21,  /*(1,-1,1)*/ 9,   /*(1,0,-1)*/ 20,  /*(1,0,0)*/ 8,   /*(1,0,1)*/ 10,
+    /*(1,1,-1)*/ 0,    /*(1,1,0)*/ 19,   /*(1,1,1)*/ 23};
 
 struct SelShared {
     float4 list[kSelWarps][kListCap];
@@ -36,11 +48,124 @@ struct SelShared {
     int warpCnt[kSelWarps][28];
     int phaseBase[28];
     int running[28];
+    int phaseCellStart[28];  // non-empty cell lists: cells of phase p are cellList[phaseCellStart[p] .. [p+1])
+    int phaseCellFill[27];
     int lo, hi, cloud, base;
 };
 
-__device__ __forceinline__ bool within_pq(float px, float py, float pz, float qx, float qy, float qz, float r) {
-    return within_radius(px, py, pz, qx, qy, qz, r);
+struct CloudCtx {
+    const int2* cells;
+    const float* pts;
+    unsigned char* sFlags;        // shared-memory flags (index: sorted position - cLo) or nullptr
+    unsigned char* gFlags;        // global flags (index: sorted position) when the cloud does not fit
+    int cLo;
+    int n;
+    float thr;                    // exact squared-distance threshold of the cloud's radius
+    __device__ __forceinline__ unsigned char flag(int j) const {
+        return sFlags ? sFlags[j - cLo] : __ldcg(&gFlags[j]);
+    }
+    __device__ __forceinline__ void set_flag(int j, unsigned char v) const {
+        if (sFlags)
+            sFlags[j - cLo] = v;
+        else
+            __stcg(&gFlags[j], v);
+    }
+};
+
+// one cell of the current phase, processed by one warp
+__device__ __forceinline__ void process_cell(const CloudCtx& cx, SelShared& sh, int warp, int lane, int x, int y, int z,
+                                             int2 own, int ph) {
+    const int n = cx.n;
+    const unsigned ltMask = (1u << lane) - 1u;
+    // ---- A: compact the accepted points of the 26 neighbour cells into the warp's list
+    int nlo = 0, nhi = 0;
+    if (lane < 27 && lane != kSelfOffset) {
+        int qx = x + kOffsPool[lane][0], qy = y + kOffsPool[lane][1], qz = z + kOffsPool[lane][2];
+        if (qx >= 0 && qx < n && qy >= 0 && qy < n && qz >= 0 && qz < n) {
+            int2 ce = cx.cells[(qx * n + qy) * n + qz];
+            nlo = ce.x;
+            nhi = ce.y;
+        }
+    }
+    if (lane == 0) sh.listCount[warp] = 0;
+    __syncwarp();
+    for (int j = nlo; j < nhi; ++j)
+        if (cx.flag(j)) {
+            int slot = atomicAdd(&sh.listCount[warp], 1);
+            if (slot < kListCap) sh.listIdx[warp][slot] = j;
+        }
+    __syncwarp();
+    int L = sh.listCount[warp];
+    bool listOk = L <= kListCap;  // else: fall back to walking the cells directly (never wrong, only slow)
+    if (listOk) {
+        for (int t = lane; t < L; t += 32) {
+            int j = sh.listIdx[warp][t];
+            sh.list[warp][t] = make_float4(cx.pts[(size_t)j * 3], cx.pts[(size_t)j * 3 + 1], cx.pts[(size_t)j * 3 + 2], 0.f);
+        }
+    }
+    __syncwarp();
+
+    // ---- B + C: own points, 32 at a time
+    for (int c0 = own.x; c0 < own.y; c0 += 32) {
+        const int cnt = min(32, own.y - c0);
+        // lanes spread over (point, list slice): pointLanes = smallest power of two >= cnt
+        int pointLanes = 1;
+        while (pointLanes < cnt) pointLanes <<= 1;
+        const int slices = 32 / pointLanes;
+        const int pi = lane & (pointLanes - 1), slice = lane / pointLanes;
+        const int i = c0 + pi;
+        const bool valid = pi < cnt;
+        float px = 0.f, py = 0.f, pz = 0.f;
+        if (valid) {
+            px = cx.pts[(size_t)i * 3];
+            py = cx.pts[(size_t)i * 3 + 1];
+            pz = cx.pts[(size_t)i * 3 + 2];
+        }
+        int blocked = 0;  // an accepted point of an earlier phase / earlier chunk lies within r
+        if (listOk) {
+            for (int t = slice; t < L; t += slices) {
+                float4 q = sh.list[warp][t];
+                blocked |= dist2_ref(px, py, pz, q.x, q.y, q.z) <= cx.thr;
+            }
+        } else {
+            for (int o = 0; o < 27; ++o) {
+                int lo2 = __shfl_sync(MC_FULL_MASK, nlo, o), hi2 = __shfl_sync(MC_FULL_MASK, nhi, o);
+                if (o == kSelfOffset) {  // earlier chunks of the own cell
+                    lo2 = own.x;
+                    hi2 = c0;
+                }
+                for (int j = lo2 + slice; j < hi2; j += slices)
+                    if (cx.flag(j))
+                        blocked |= dist2_ref(px, py, pz, cx.pts[(size_t)j * 3], cx.pts[(size_t)j * 3 + 1],
+                                             cx.pts[(size_t)j * 3 + 2]) <= cx.thr;
+            }
+        }
+        for (int off = pointLanes; off < 32; off <<= 1) blocked |= __shfl_xor_sync(MC_FULL_MASK, blocked, off);
+        // C: order dependence inside the chunk, walking only the unblocked points in ascending order; lanes
+        // 0..cnt-1 (slice 0) hold the points
+        const bool holder = lane < cnt;  // slice 0 lanes: pi == lane
+        unsigned cand = __ballot_sync(MC_FULL_MASK, holder && !blocked);
+        bool mySel = false;
+        while (cand) {
+            const int u = __ffs(cand) - 1;
+            cand &= cand - 1;
+            const float ux = __shfl_sync(MC_FULL_MASK, px, u);
+            const float uy = __shfl_sync(MC_FULL_MASK, py, u);
+            const float uz = __shfl_sync(MC_FULL_MASK, pz, u);
+            const bool hit = holder && lane < u && mySel && dist2_ref(ux, uy, uz, px, py, pz) <= cx.thr;
+            const unsigned any = __ballot_sync(MC_FULL_MASK, hit);
+            if (lane == u) mySel = (any == 0);
+        }
+        if (holder && mySel) cx.set_flag(i, (unsigned char)(ph + 1));
+        if (c0 + 32 < own.y && listOk) {  // later chunks of this cell must see this chunk's accepted points
+            const unsigned selMask = __ballot_sync(MC_FULL_MASK, holder && mySel);
+            const int pos = L + __popc(selMask & ltMask);
+            if (holder && mySel && pos < kListCap) sh.list[warp][pos] = make_float4(px, py, pz, 0.f);
+            L += __popc(selMask);
+            if (L > kListCap) listOk = false;
+        }
+        __syncwarp();
+    }
 }
 
 __global__ void __launch_bounds__(kSelThreads)
@@ -52,21 +177,29 @@ __global__ void __launch_bounds__(kSelThreads)
     extern __shared__ __align__(16) unsigned char smemRaw[];
     SelShared& sh = *reinterpret_cast<SelShared*>(smemRaw);
     unsigned char* sFlags = smemRaw + sizeof(SelShared);
+    unsigned short* cellList = reinterpret_cast<unsigned short*>(sFlags + kSelFlagBytes);
     const int lane = lane_id(), warp = threadIdx.x >> 5;
     const unsigned ltMask = (1u << lane) - 1u;
 
-    // claim a cloud: ticket order == start order, so waiting on the predecessor at the end cannot deadlock
+    // claim a cloud: ticket order == start order, so the look-back at the end only waits for running CTAs
     if (threadIdx.x == 0) {
         sh.cloud = lookback_ticket(chain);
         sh.lo = INT_MAX;
         sh.hi = 0;
     }
+    if (threadIdx.x < 28) {
+        sh.phaseBase[threadIdx.x] = 0;
+        sh.running[threadIdx.x] = 0;
+        sh.phaseCellStart[threadIdx.x] = 0;
+        if (threadIdx.x < 27) sh.phaseCellFill[threadIdx.x] = 0;
+    }
     __syncthreads();
     const int b = sh.cloud;
     const int cellsPerCloud = n * n * n;
     const int2* cells = cellIdx + (size_t)b * cellsPerCloud;
+    const bool useLists = cellsPerCloud <= kCellListCap;
 
-    // extent of this cloud inside the sorted array (the sort is batch-major)
+    // extent of this cloud inside the sorted array (the sort is batch-major) + non-empty cells per phase
     {
         int lo = INT_MAX, hi = 0;
         for (int c = threadIdx.x; c < cellsPerCloud; c += kSelThreads) {
@@ -74,6 +207,11 @@ __global__ void __launch_bounds__(kSelThreads)
             if (ce.y > ce.x) {
                 lo = min(lo, ce.x);
                 hi = max(hi, ce.y);
+                if (useLists) {
+                    const int x = c / (n * n), y = (c / n) % n, z = c % n;
+                    const int p = kPhaseOfOffset[(x % 3) * 9 + (y % 3) * 3 + (z % 3)];  // offset = coord % 3 - 1
+                    atomicAdd(&sh.phaseCellStart[p + 1], 1);
+                }
             }
         }
         lo = __reduce_min_sync(MC_FULL_MASK, lo);
@@ -87,111 +225,62 @@ __global__ void __launch_bounds__(kSelThreads)
     const int cLo = sh.lo, cHi = sh.hi;
     const int nCloud = cHi > cLo ? cHi - cLo : 0;
     const bool inSmem = nCloud <= kSelFlagBytes;
-    // flags addressed by sorted position; volatile: written and read by different warps between barriers
-    volatile unsigned char* flags = inSmem ? (sFlags - cLo) : selGlobal;
     if (inSmem)
         for (int t = threadIdx.x; t < nCloud; t += kSelThreads) sFlags[t] = 0;
-    if (threadIdx.x < 28) {
-        sh.phaseBase[threadIdx.x] = 0;
-        sh.running[threadIdx.x] = 0;
+    if (useLists) {
+        if (threadIdx.x == 0) {
+            int run = 0;
+            for (int p = 1; p <= 27; ++p) {
+                run += sh.phaseCellStart[p];
+                sh.phaseCellStart[p] = run;
+            }
+        }
+        __syncthreads();
+        for (int c = threadIdx.x; c < cellsPerCloud; c += kSelThreads) {
+            int2 ce = cells[c];
+            if (ce.y > ce.x) {
+                const int x = c / (n * n), y = (c / n) % n, z = c % n;
+                const int p = kPhaseOfOffset[(x % 3) * 9 + (y % 3) * 3 + (z % 3)];
+                cellList[sh.phaseCellStart[p] + atomicAdd(&sh.phaseCellFill[p], 1)] = (unsigned short)c;
+            }
+        }
     }
     __syncthreads();
 
-    const float ext = max_extent(mn, mx, b);
-    const float r = scaleInv ? __fmul_rn(radius, ext) : radius;
+    CloudCtx cx;
+    cx.cells = cells;
+    cx.pts = pts;
+    cx.sFlags = inSmem ? sFlags : nullptr;
+    cx.gFlags = selGlobal;
+    cx.cLo = cLo;
+    cx.n = n;
+    {
+        const float ext = max_extent(mn, mx, b);
+        cx.thr = exact_radius_threshold(scaleInv ? __fmul_rn(radius, ext) : radius);
+    }
 
     if (nCloud > 0) {
         for (int ph = 0; ph < 27; ++ph) {
-            const int ox = kOffsPool[ph][0], oy = kOffsPool[ph][1], oz = kOffsPool[ph][2];
-            // cells of this phase: 3t+1+o < n  (only the upper bound exists, poisson_sampling.cu:70-74)
-            const int tX = (n + 1 - ox) / 3, tY = (n + 1 - oy) / 3, tZ = (n + 1 - oz) / 3;
-            const int total = tX * tY * tZ;
-            for (int c = warp; c < total; c += kSelWarps) {
-                const int tx = c / (tY * tZ), rem = c - tx * (tY * tZ);
-                const int ty = rem / tZ, tz = rem - ty * tZ;
-                const int x = tx * 3 + 1 + ox, y = ty * 3 + 1 + oy, z = tz * 3 + 1 + oz;
-                const int2 own = cells[(x * n + y) * n + z];
-                if (own.y <= own.x) continue;
-
-                // ---- A: compact the accepted points of the 26 neighbour cells into the warp's list
-                int nlo = 0, nhi = 0;
-                if (lane < 27 && lane != kSelfOffset) {
-                    int qx = x + kOffsPool[lane][0], qy = y + kOffsPool[lane][1], qz = z + kOffsPool[lane][2];
-                    if (qx >= 0 && qx < n && qy >= 0 && qy < n && qz >= 0 && qz < n) {
-                        int2 ce = cells[(qx * n + qy) * n + qz];
-                        nlo = ce.x;
-                        nhi = ce.y;
-                    }
+            if (useLists) {
+                const int beg = sh.phaseCellStart[ph], end = sh.phaseCellStart[ph + 1];
+                for (int t = beg + warp; t < end; t += kSelWarps) {
+                    const int c = cellList[t];
+                    const int x = c / (n * n), y = (c / n) % n, z = c % n;
+                    process_cell(cx, sh, warp, lane, x, y, z, cells[c], ph);
                 }
-                if (lane == 0) sh.listCount[warp] = 0;
-                __syncwarp();
-                for (int j = nlo; j < nhi; ++j)
-                    if (flags[j]) {
-                        int slot = atomicAdd(&sh.listCount[warp], 1);
-                        if (slot < kListCap) sh.listIdx[warp][slot] = j;
-                    }
-                __syncwarp();
-                int L = sh.listCount[warp];
-                bool listOk = L <= kListCap;  // else: fall back to walking the cells directly (never wrong, only slow)
-                if (listOk) {
-                    for (int t = lane; t < L; t += 32) {
-                        int j = sh.listIdx[warp][t];
-                        sh.list[warp][t] =
-                            make_float4(pts[(size_t)j * 3], pts[(size_t)j * 3 + 1], pts[(size_t)j * 3 + 2], 0.f);
-                    }
-                }
-                __syncwarp();
-
-                // ---- B: own points, 32 at a time, one per lane
-                for (int c0 = own.x; c0 < own.y; c0 += 32) {
-                    const int i = c0 + lane;
-                    const bool valid = i < own.y;
-                    float px = 0.f, py = 0.f, pz = 0.f;
-                    if (valid) {
-                        px = pts[(size_t)i * 3];
-                        py = pts[(size_t)i * 3 + 1];
-                        pz = pts[(size_t)i * 3 + 2];
-                    }
-                    bool blocked = false;  // an accepted point of an earlier phase / earlier chunk lies within r
-                    if (listOk) {
-                        for (int t = 0; t < L; ++t) {
-                            float4 q = sh.list[warp][t];
-                            blocked |= within_pq(px, py, pz, q.x, q.y, q.z, r);
-                        }
-                    } else {
-                        for (int o = 0; o < 27; ++o) {
-                            int lo2 = __shfl_sync(MC_FULL_MASK, nlo, o), hi2 = __shfl_sync(MC_FULL_MASK, nhi, o);
-                            if (o == kSelfOffset) {  // earlier chunks of the own cell
-                                lo2 = own.x;
-                                hi2 = c0;
-                            }
-                            for (int j = lo2; j < hi2; ++j)
-                                if (flags[j])
-                                    blocked |= within_pq(px, py, pz, pts[(size_t)j * 3], pts[(size_t)j * 3 + 1],
-                                                         pts[(size_t)j * 3 + 2], r);
-                        }
-                    }
-                    // order dependence inside the chunk: point u is rejected by an accepted earlier point within r
-                    const int cnt = min(32, own.y - c0);
-                    bool mySel = false;
-                    for (int u = 0; u < cnt; ++u) {
-                        float ux = __shfl_sync(MC_FULL_MASK, px, u);
-                        float uy = __shfl_sync(MC_FULL_MASK, py, u);
-                        float uz = __shfl_sync(MC_FULL_MASK, pz, u);
-                        int ub = __shfl_sync(MC_FULL_MASK, (int)blocked, u);
-                        bool hit = lane < u && mySel && within_pq(ux, uy, uz, px, py, pz, r);
-                        unsigned any = __ballot_sync(MC_FULL_MASK, hit);
-                        if (lane == u) mySel = (ub == 0) && (any == 0);
-                    }
-                    if (valid && mySel) flags[i] = (unsigned char)(ph + 1);
-                    if (c0 + 32 < own.y && listOk) {  // later chunks of this cell must see this chunk's accepted points
-                        unsigned selMask = __ballot_sync(MC_FULL_MASK, valid && mySel);
-                        int pos = L + __popc(selMask & ltMask);
-                        if (valid && mySel && pos < kListCap) sh.list[warp][pos] = make_float4(px, py, pz, 0.f);
-                        L += __popc(selMask);
-                        if (L > kListCap) listOk = false;
-                    }
-                    __syncwarp();
+                if (end == beg) continue;  // nothing was written in this phase: no barrier needed (uniform)
+            } else {
+                const int ox = kOffsPool[ph][0], oy = kOffsPool[ph][1], oz = kOffsPool[ph][2];
+                // cells of this phase: 3t+1+o < n  (only the upper bound exists, poisson_sampling.cu:70-74)
+                const int tX = (n + 1 - ox) / 3, tY = (n + 1 - oy) / 3, tZ = (n + 1 - oz) / 3;
+                const int total = tX * tY * tZ;
+                for (int c = warp; c < total; c += kSelWarps) {
+                    const int tx = c / (tY * tZ), rem = c - tx * (tY * tZ);
+                    const int ty = rem / tZ, tz = rem - ty * tZ;
+                    const int x = tx * 3 + 1 + ox, y = ty * 3 + 1 + oy, z = tz * 3 + 1 + oz;
+                    const int2 own = cells[(x * n + y) * n + z];
+                    if (own.y <= own.x) continue;
+                    process_cell(cx, sh, warp, lane, x, y, z, own, ph);
                 }
             }
             __syncthreads();
@@ -199,25 +288,25 @@ __global__ void __launch_bounds__(kSelThreads)
 
         // ---- stable compaction by (phase, position): tmpIdx[cLo + rank] = position
         for (int t = threadIdx.x; t < nCloud; t += kSelThreads) {
-            int f = flags[cLo + t];
-            if (f) atomicAdd(&sh.phaseBase[f], 1);  // histogram at [f] so that the exclusive scan lands at [f-1]...
+            int f = cx.flag(cLo + t);
+            if (f) atomicAdd(&sh.phaseBase[f], 1);
         }
         __syncthreads();
-        if (threadIdx.x == 0) {  // phaseBase[f] <- number of accepted points in phases < f-1 ... i.e. exclusive scan
+        if (threadIdx.x == 0) {  // phaseBase[f] <- first output slot of phase f-1; phaseBase[0] <- cloud total
             int run = 0;
             for (int f = 1; f <= 27; ++f) {
                 int cntF = sh.phaseBase[f];
                 sh.phaseBase[f] = run;
                 run += cntF;
             }
-            sh.phaseBase[0] = run;  // total accepted points of the cloud
+            sh.phaseBase[0] = run;
         }
         __syncthreads();
         for (int t0 = 0; t0 < nCloud; t0 += kSelThreads) {
             for (int e = threadIdx.x; e < kSelWarps * 28; e += kSelThreads) (&sh.warpCnt[0][0])[e] = 0;
             __syncthreads();
             const int t = t0 + threadIdx.x;
-            const int f = t < nCloud ? flags[cLo + t] : 0;
+            const int f = t < nCloud ? cx.flag(cLo + t) : 0;
             const unsigned grp = __match_any_sync(MC_FULL_MASK, f);
             if (f && lane == __ffs(grp) - 1) sh.warpCnt[warp][f] = __popc(grp);
             __syncthreads();
@@ -262,6 +351,8 @@ __global__ void __launch_bounds__(kSelThreads)
     }
 }
 
+constexpr size_t kSelSmemBytes = sizeof(SelShared) + kSelFlagBytes + kCellListCap * sizeof(unsigned short);
+
 }  // namespace
 }  // namespace mc
 
@@ -286,12 +377,12 @@ extern "C" int mc_poisson_sampling(int scaleInv, float radius, int numPoints, co
     (void)batchIds;
     MC_REQUIRE(radius > 0.0f, "mc_poisson_sampling: radius must be positive");
     MC_REQUIRE(batchSize > 0 && numCells > 0, "mc_poisson_sampling: batch size and cell count must be positive");
+    MC_REQUIRE(numCells <= 1290, "mc_poisson_sampling: grid too fine (cell index would overflow)");
     MC_REQUIRE(dNumSamples != nullptr, "mc_poisson_sampling: dNumSamples required");
     cudaStream_t s = (cudaStream_t)stream;
-    const size_t smem = sizeof(SelShared) + kSelFlagBytes;
     static bool attrSet = false;
     if (!attrSet) {
-        cudaFuncSetAttribute(poisson_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(poisson_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSelSmemBytes);
         attrSet = true;
     }
     const long long N = numPoints > 0 ? numPoints : 1;
@@ -302,7 +393,7 @@ extern "C" int mc_poisson_sampling(int scaleInv, float radius, int numPoints, co
     int* tmpIdx = workspace + descInts + (N / 4 + 1);
     cudaMemsetAsync(workspace, 0, sizeof(int) * (size_t)(descInts + (N / 4 + 1)), s);  // descriptors + flags
     if (numPoints > 0) {
-        poisson_kernel<<<batchSize, kSelThreads, smem, s>>>(
+        poisson_kernel<<<batchSize, kSelThreads, kSelSmemBytes, s>>>(
             scaleInv != 0, radius, batchSize, numCells, aabbMin, aabbMax, pts, reinterpret_cast<const int2*>(cellIdx),
             sel, tmpIdx, chain, capacityOut, outPts, outBatchIds, outIdx, dNumSamples, dOverflow);
     } else {
