@@ -28,6 +28,34 @@ def _log(msg):
         print(msg)
 
 
+class _LazyList:
+    """List whose elements may be zero-argument thunks evaluated (once) on first access."""
+
+    def __init__(self, items=()):
+        self._items = [(True, v) for v in items]
+
+    def append(self, value):
+        self._items.append((True, value))
+
+    def append_lazy(self, thunk):
+        self._items.append((False, thunk))
+
+    def __len__(self):
+        return len(self._items)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[k] for k in range(*i.indices(len(self._items)))]
+        ready, v = self._items[i]
+        if not ready:
+            v = v()
+            self._items[i] = (True, v)
+        return v
+
+    def __iter__(self):
+        return (self[k] for k in range(len(self._items)))
+
+
 class PointHierarchy:
     """Poisson-disk point hierarchy of a packed batch (utils/MCConvBuilder.py:24-131).
 
@@ -37,37 +65,46 @@ class PointHierarchy:
     def __init__(self, inPoints, inFeatures, inBatchIds, radiusList, hierarchyName="Point_Hierarchy", batchSize=32,
                  relativeRadius=True):
         self.points_ = [inPoints]
-        self.features_ = [inFeatures]
+        self.features_ = _LazyList([inFeatures])
         self.batchIds_ = [inBatchIds]
-        self.sampledIndexs_ = []
+        self.sampledIndexs_ = _LazyList()
         self.radiusList_ = [0.0]
         self.batchSize_ = batchSize
         self.relativeRadius_ = relativeRadius
         self.hierarchyName_ = hierarchyName
 
+        with _rt.lane("hier"):  # the hierarchy chain runs on its own stream in planned mode
+            self._build(inPoints, inBatchIds, radiusList, batchSize)
+
+    def _build(self, inPoints, inBatchIds, radiusList, batchSize):
+        hierarchyName, relativeRadius = self.hierarchyName_, self.relativeRadius_
         aabbMin, aabbMax = compute_aabb(inPoints, inBatchIds, batchSize, self.relativeRadius_)
         self.aabbMin_ = aabbMin
         self.aabbMax_ = aabbMax
 
         _log("########## Point Hierarchy: " + hierarchyName + " (Rel: " + str(relativeRadius) + ")")
-        currPts, currFeatures, currBatchIds = inPoints, inFeatures, inBatchIds
+        currPts, currBatchIds = inPoints, inBatchIds
         for level, currRadius in enumerate(radiusList):
             _log("Level: " + str(level + 1) + " | Poisson Disk Radius: " + str(currRadius))
-            # sort_points_step1 + sort_points_step2 (utils/MCConvBuilder.py:106-110), fused into one launch
-            keys, indexs, sortPts, sortBatchs, sortFeatures, cellIndexs = sort_points(
-                currPts, currBatchIds, currFeatures, self.aabbMin_, self.aabbMax_, self.batchSize_, currRadius,
+            # sort_points_step1 + sort_points_step2 (utils/MCConvBuilder.py:106-110), fused into one launch.  Only the
+            # geometry is sorted here: the per-level features and the transformed sample indices
+            # (utils/MCConvBuilder.py:115-116) are derived on first access -- no MC* model reads sampledIndexs_ and
+            # only MCClassH reads features_[1], so the common forward pays for neither.
+            noFeatures = currPts.new_empty((currPts.shape[0], 0))
+            keys, indexs, sortPts, sortBatchs, _, cellIndexs = sort_points(
+                currPts, currBatchIds, noFeatures, self.aabbMin_, self.aabbMax_, self.batchSize_, currRadius,
                 self.relativeRadius_)
             sampledPts, sampledBatchsIds, sampledIndexs = poisson_sampling(
                 sortPts, sortBatchs, cellIndexs, aabbMin, aabbMax, currRadius, batchSize, self.relativeRadius_)
-            sampledFeatures = get_sampled_features(sampledIndexs, sortFeatures)
-            transformedIndexs = transform_indexs(sampledIndexs, indexs)
 
             self.points_.append(sampledPts)
             self.batchIds_.append(sampledBatchsIds)
-            self.features_.append(sampledFeatures)
-            self.sampledIndexs_.append(transformedIndexs)
+            self.features_.append_lazy(
+                lambda lvl=level, si=sampledIndexs, ix=indexs: get_sampled_features(
+                    si, sort_features(self.features_[lvl], ix)))
+            self.sampledIndexs_.append_lazy(lambda si=sampledIndexs, ix=indexs: transform_indexs(si, ix))
             self.radiusList_.append(currRadius)
-            currPts, currBatchIds, currFeatures = sampledPts, sampledBatchsIds, sampledFeatures
+            currPts, currBatchIds = sampledPts, sampledBatchsIds
 
 
 class ConvolutionBuilder:
@@ -126,16 +163,28 @@ class ConvolutionBuilder:
 
         ph = inPointHierarchy
         # grid: cache hit -> only re-sort the new features into the cached order (utils/MCConvBuilder.py:349-351)
-        if keyGrid in self.cacheGrids_:
-            currGridTuple = self.cacheGrids_[keyGrid]
-            sortFeatures = sort_features(inFeatures, currGridTuple[3])
-        else:
-            # sort_points_step1 + sort_points_step2 (utils/MCConvBuilder.py:353-361), fused into one launch
-            keys, indexs, sortPts, sortBatchs, sortFeatures, cellIndexs = sort_points(
-                ph.points_[inPointLevel], ph.batchIds_[inPointLevel], inFeatures, ph.aabbMin_, ph.aabbMax_,
+        with _rt.lane("geom"):  # grid, neighbour list and pdf never touch the features: separate stream
+            currGridTuple, currNeighTuple, currPDFs = self._geometry(
+                ph, inPointLevel, currOutPointHierarchy, currOutPointLevel, convRadius, currRelativeRadius,
+                currKDEWindow, currUsePDF, keyGrid, keyNeighs, keyPDF)
+        sortFeatures = sort_features(inFeatures, currGridTuple[3])
+        return self._convolve(convName, ph, currGridTuple, currNeighTuple, currPDFs, sortFeatures, inNumFeatures,
+                              currNumOutFeatures, currMultiFeatureConv, currOutPointHierarchy, currOutPointLevel,
+                              convRadius, currRelativeRadius, currUseAVG)
+
+    def _geometry(self, ph, inPointLevel, currOutPointHierarchy, currOutPointLevel, convRadius, currRelativeRadius,
+                  currKDEWindow, currUsePDF, keyGrid, keyNeighs, keyPDF):
+        if keyGrid not in self.cacheGrids_:
+            # sort_points_step1 + sort_points_step2 (utils/MCConvBuilder.py:353-361), fused into one launch.  The grid
+            # is pure geometry (it does not depend on the features), so it is built without them and the features
+            # are always brought into grid order by sort_features -- what the reference does on a cache hit.  This
+            # keeps every geometric op independent of the feature chain (they overlap on separate streams).
+            pts = ph.points_[inPointLevel]
+            keys, indexs, sortPts, sortBatchs, _, cellIndexs = sort_points(
+                pts, ph.batchIds_[inPointLevel], pts.new_empty((pts.shape[0], 0)), ph.aabbMin_, ph.aabbMax_,
                 ph.batchSize_, convRadius, currRelativeRadius)
-            currGridTuple = (sortPts, sortBatchs, cellIndexs, indexs)
-            self.cacheGrids_[keyGrid] = currGridTuple
+            self.cacheGrids_[keyGrid] = (sortPts, sortBatchs, cellIndexs, indexs)
+        currGridTuple = self.cacheGrids_[keyGrid]
 
         if keyNeighs in self.cacheNeighs_:
             currNeighTuple = self.cacheNeighs_[keyNeighs]
@@ -159,7 +208,11 @@ class ConvolutionBuilder:
                 currPDFs = _rt.tag(torch.ones((neigh.shape[0], 1), dtype=torch.float32, device=neigh.device),
                                    _rt.count_of(neigh))
             self.cachePDFs_[keyPDF] = currPDFs
+        return currGridTuple, currNeighTuple, currPDFs
 
+    def _convolve(self, convName, ph, currGridTuple, currNeighTuple, currPDFs, sortFeatures, inNumFeatures,
+                  currNumOutFeatures, currMultiFeatureConv, currOutPointHierarchy, currOutPointLevel, convRadius,
+                  currRelativeRadius, currUseAVG):
         # parameters (utils/MCConvBuilder.py:394-419)
         vs = self.variables_
         blockSize = get_block_size()

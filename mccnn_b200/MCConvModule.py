@@ -28,6 +28,18 @@ def _req(cond, msg):
         raise ValueError(msg)
 
 
+def _scheduled(fn):
+    """Route an op through runtime.dispatch: in planned multi-stream mode it runs on the stream of the current lane
+    (hierarchy / convolution geometry / features) with event dependencies on its tensor inputs; otherwise it is a
+    plain call on the current stream."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        return _rt.dispatch([a for a in args if isinstance(a, torch.Tensor)], lambda: fn(*args, **kwargs))
+    return wrapper
+
+
 def _check_points(t, name):
     _req(t.dim() == 2 and t.shape[1] >= 3, name + " expects points with at least three components")
 
@@ -45,6 +57,7 @@ def get_block_size():
     return ops.get_block_size()
 
 
+@_scheduled
 def compute_aabb(inPts, inBatchIds, batchSize, scaleInv=True):
     """ComputeAabb, tf_ops/aabb_gpu.cc:22-84 -> (aabbMin [B,3], aabbMax [B,3])."""
     _req(batchSize > 0, "ComputeAabb expects a positive batch size")
@@ -59,6 +72,7 @@ def _num_cells(aabbMin, aabbMax, cellSize, scaleInv):
     return ops.num_cells(cellSize, scaleInv, aabbMin, aabbMax)
 
 
+@_scheduled
 def sort_points_step1(inPts, inBatchIds, aabbMin, aabbMax, batchSize, cellSize, scaleInv):
     """SortPointsStep1, tf_ops/sort_gpu.cc:23-38,184-268 -> (keys [N], indexs [N])."""
     _req(batchSize > 0, "SortPointsStep1 expects a positive batch size")
@@ -71,6 +85,7 @@ def sort_points_step1(inPts, inBatchIds, aabbMin, aabbMax, batchSize, cellSize, 
     return _tag(keys, nd), _tag(idx, nd)
 
 
+@_scheduled
 def sort_points_step2(inPts, inBatchIds, inFeatures, keys, indexs, aabbMin, aabbMax, batchSize, cellSize, scaleInv):
     """SortPointsStep2, tf_ops/sort_gpu.cc:40-64,270-378 -> (pts [N,3], batchIds [N,1], features [N,C], cellIndexs)."""
     _req(batchSize > 0, "SortPointsStep2 expects a positive batch size")
@@ -87,6 +102,7 @@ def sort_points_step2(inPts, inBatchIds, inFeatures, keys, indexs, aabbMin, aabb
     return _tag(p, nd), _tag(b.reshape(-1, 1), nd), _tag(f, nd), cells
 
 
+@_scheduled
 def sort_points(inPts, inBatchIds, inFeatures, aabbMin, aabbMax, batchSize, cellSize, scaleInv):
     """sort_points_step1 followed by sort_points_step2 (the only way the reference ever uses them,
     utils/MCConvBuilder.py:106-110,353-361) -> (keys, indexs, sortPts, sortBatchIds, sortFeatures, cellIndexs).
@@ -124,6 +140,7 @@ def sort_points(inPts, inBatchIds, inFeatures, aabbMin, aabbMax, batchSize, cell
     return _tag(keys, nd), _tag(idx, nd), _tag(p, nd), _tag(b.reshape(-1, 1), nd), _tag(f, nd), cells
 
 
+@_scheduled
 def sort_features(inFeatures, indexs):
     """python sort_features -> SortFeaturesBackGrad op (MCConvModuleSrc:35-36): out[indexs[i]] = inFeatures[i]."""
     _req(inFeatures.dim() == 2, "SortFeaturesBackGrad expects features of shape (numPoints, C)")
@@ -132,6 +149,7 @@ def sort_features(inFeatures, indexs):
     return _tag(ops.sort_features(inFeatures, indexs, _cnt(indexs)), _cnt(indexs))
 
 
+@_scheduled
 def sort_features_back(inFeatures, indexs):
     """SortFeaturesBack, tf_ops/sort_gpu.cc:78-85: out[i] = inFeatures[indexs[i]]."""
     _req(inFeatures.dim() == 2, "SortFeaturesBack expects features of shape (numPoints, C)")
@@ -140,6 +158,7 @@ def sort_features_back(inFeatures, indexs):
     return _tag(ops.sort_features_back(inFeatures, indexs, _cnt(indexs)), _cnt(indexs))
 
 
+@_scheduled
 def transform_indexs(inIndexs, inNewPositions):
     """TransformIndexs, tf_ops/sort_gpu.cc:96-103,496-533."""
     _req(inIndexs.dim() == 1 and inNewPositions.dim() == 1, "TransformIndexs expects one-dimensional index tensors")
@@ -147,6 +166,7 @@ def transform_indexs(inIndexs, inNewPositions):
     return _tag(ops.transform_indexs(inIndexs, inNewPositions, md, _cnt(inNewPositions)), md)
 
 
+@_scheduled
 def find_neighbors(inPts, inBatchIds, inPts2, cellIndexs, aabbMin, aabbMax, radius, batchSize, scaleInv):
     """FindNeighbors, tf_ops/find_neighbors.cc:25-43,93-185 -> (startIndexs [M,1], neighIndexs [K,2])."""
     _req(radius > 0.0, "FindNeighborsOp expects a positive radius")
@@ -174,6 +194,7 @@ def find_neighbors(inPts, inBatchIds, inPts2, cellIndexs, aabbMin, aabbMax, radi
     return start.reshape(-1, 1), pairs
 
 
+@_scheduled
 def compute_pdf(inPts, inBatchIds, aabbMin, aabbMax, startIndexs, neighbors, window, radius, batchSize, scaleInv):
     """ComputePDF, tf_ops/compute_pdf.cc:25-41,57-142 -> pdfs [K,1]."""
     _req(window > 0.0, "ComputePDFOp expects a positive window")
@@ -190,6 +211,7 @@ def compute_pdf(inPts, inBatchIds, aabbMin, aabbMax, startIndexs, neighbors, win
     return _tag(pdf.reshape(-1, 1), kd)
 
 
+@_scheduled
 def poisson_sampling(inPts, inBatchIds, cellIndexs, aabbMin, aabbMax, radius, batchSize, scaleInv):
     """PoissonSampling, tf_ops/poisson_sampling.cc:26-45,109-211 -> (pts [M,3], batchIds [M,1], indexs [M])."""
     _req(radius > 0.0, "PoissonSamplingOp expects a positive radius")
@@ -213,6 +235,7 @@ def poisson_sampling(inPts, inBatchIds, cellIndexs, aabbMin, aabbMax, radius, ba
     return p[:M].clone(), b[:M].clone().reshape(-1, 1), idx[:M].clone()
 
 
+@_scheduled
 def get_sampled_features(inSampledIndexs, pInFeatures):
     """GetSampledFeatures, tf_ops/poisson_sampling.cc:47-55,213-250."""
     _req(inSampledIndexs.dim() == 1, "GetSampledFeaturesOp expects indexs of shape (numSamples)")
@@ -221,6 +244,7 @@ def get_sampled_features(inSampledIndexs, pInFeatures):
     return _tag(ops.get_sampled_features(inSampledIndexs, pInFeatures, md), md)
 
 
+@_scheduled
 def spatial_conv(inPts, inFeatures, inBatchIds, inPDFs, inSamplePts, neighStartIndexs, packedNeighs, aabbMin, aabbMax,
                  weights1, weights2, weightsOut, biases1, biases2, biasesOut, numOutFeatures, combin, batchSize,
                  radius, scaleInv, avg):

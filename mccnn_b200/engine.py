@@ -19,9 +19,11 @@ from . import runtime as _rt
 
 
 class PlannedForward:
-    def __init__(self, fn, out_rows, use_graph=True, slack=1.3):
-        """fn(points, batchIds, features) -> [>= out_rows, F] tensor; out_rows rows of it are the result."""
+    def __init__(self, fn, out_rows, use_graph=True, slack=1.3, multistream=True):
+        """fn(points, batchIds, features) -> [>= out_rows, F] tensor; out_rows rows of it are the result.
+        multistream: overlap the hierarchy / convolution-geometry / feature chains on three streams (runtime.planned)."""
         self.fn = fn
+        self.multistream = multistream
         self.out_rows = out_rows
         self.use_graph = use_graph
         self.slack = slack
@@ -43,7 +45,7 @@ class PlannedForward:
         return out[: self.out_rows]
 
     def _planned(self, pts, bids, feats):
-        with _rt.planned(self.plan, pts.device):
+        with _rt.planned(self.plan, pts.device, multistream=self.multistream):
             return self.fn(pts, bids, feats)
 
     def _capture(self, pts, bids, feats):

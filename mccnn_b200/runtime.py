@@ -58,9 +58,14 @@ class Plan:
 class _State:
     mode = "exact"   # "exact" | "record" | "planned"
     plan = None
+    lane = "main"    # "main" (features, dense glue) | "hier" (point hierarchy) | "geom" (convolution geometry)
+    streams = None   # {lane: torch.cuda.Stream} while a multi-stream planned run is active
+    forked = None    # side streams that joined the run so far
+    start_event = None
 
 
 _state = _State()
+_side_streams = {}   # (device index, lane) -> torch.cuda.Stream, created once
 
 
 def mode():
@@ -84,14 +89,92 @@ def record(slack=1.3):
 
 
 @contextlib.contextmanager
-def planned(plan, device=None):
-    prev = (_state.mode, _state.plan)
-    plan.begin(torch.device("cuda", torch.cuda.current_device()) if device is None else device)
+def planned(plan, device=None, multistream=True):
+    """Sync-free execution against `plan`.  With multistream, the three independent chains of a forward --
+    hierarchy (sort + Poisson sampling per level), convolution geometry (grid, neighbour list, pdf) and features
+    (feature re-sort, spatial_conv, dense glue) -- are issued on three streams linked by events, so they overlap on
+    the GPU; captured in a CUDA graph this becomes a DAG instead of a chain.  All side streams are joined back into
+    the caller's stream when the context exits."""
+    prev = (_state.mode, _state.plan, _state.streams, _state.forked, _state.start_event)
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+    plan.begin(device)
     _state.mode, _state.plan = "planned", plan
+    if multistream:
+        streams = {}
+        for ln in ("hier", "geom"):
+            key = (device.index, ln)
+            if key not in _side_streams:
+                _side_streams[key] = torch.cuda.Stream(device=device)
+            streams[ln] = _side_streams[key]
+        _state.streams, _state.forked = streams, []
+        _state.start_event = torch.cuda.Event()
+        _state.start_event.record(torch.cuda.current_stream(device))
+    else:
+        _state.streams, _state.forked, _state.start_event = None, None, None
     try:
         yield plan
     finally:
-        _state.mode, _state.plan = prev
+        if _state.forked:
+            main = torch.cuda.current_stream(device)
+            for s in _state.forked:  # join
+                ev = torch.cuda.Event()
+                ev.record(s)
+                main.wait_event(ev)
+        _state.mode, _state.plan, _state.streams, _state.forked, _state.start_event = prev
+
+
+@contextlib.contextmanager
+def lane(name):
+    """Declares which chain the ops issued inside belong to (used by MCConvBuilder)."""
+    prev = _state.lane
+    _state.lane = name
+    try:
+        yield
+    finally:
+        _state.lane = prev
+
+
+def _tensors(out):
+    if isinstance(out, torch.Tensor):
+        return [out]
+    if isinstance(out, (tuple, list)):
+        return [o for o in out if isinstance(o, torch.Tensor)]
+    return []
+
+
+def dispatch(inputs, fn):
+    """Run fn() on the stream of the current lane.  Outside multi-stream planned mode this is fn().  Otherwise the
+    stream first waits for the readiness events of the tensor inputs produced on other streams, and the outputs are
+    tagged with an event recorded after fn() so that consumers on other streams can wait for them."""
+    if _state.streams is None:
+        return fn()
+    main = torch.cuda.current_stream()
+    s = _state.streams.get(_state.lane)
+    if s is None:  # main lane: wait for side-stream producers
+        for t in inputs:
+            ev = getattr(t, "_mc_ev", None)
+            if ev is not None:
+                main.wait_event(ev)
+                if t.is_cuda:
+                    t.record_stream(main)
+        return fn()
+    if s not in _state.forked:  # fork: the side stream starts after everything already queued on the main stream
+        s.wait_event(_state.start_event)
+        _state.forked.append(s)
+    with torch.cuda.stream(s):
+        for t in inputs:
+            ev = getattr(t, "_mc_ev", None)
+            if ev is not None and getattr(t, "_mc_stream", None) is not s:
+                s.wait_event(ev)
+            if t.is_cuda:
+                t.record_stream(s)
+        out = fn()
+        ev = torch.cuda.Event()
+        ev.record(s)
+    for o in _tensors(out):
+        o._mc_ev = ev
+        o._mc_stream = s
+    return out
 
 
 def count_of(t):
