@@ -96,6 +96,14 @@ int mc_find_neighbors_pack(int scaleInv, int numSamples, const int* dNumSamples,
                            const float* aabbMin, const float* aabbMax, int* startIdx, const int* workspace,
                            int* pairs, int capacityPairs, int* dOverflow, void* stream);
 
+/* countNeighborsCPU + packNeighborsCPU in ONE launch (no intermediate scan kernels, distances evaluated once) for
+ * callers that provide the pair capacity up front.  startIdx receives the final start indices, *dNumNeighbors the
+ * total.  workspace: mc_find_neighbors_workspace_ints ints, 8-byte aligned. */
+int mc_find_neighbors_fused(int scaleInv, int numSamples, const int* dNumSamples, int numCells, float radius,
+                            const float* samples, const int* sampleBatchIds, const float* pts2, const int* cellIdx,
+                            const float* aabbMin, const float* aabbMax, int* startIdx, int* workspace, int* pairs,
+                            int capacityPairs, int* dNumNeighbors, int* dOverflow, void* stream);
+
 /* computeDPFsCPU -- tf_ops/compute_pdf.cc:43-55, tf_ops/compute_pdf.cu:98-120 */
 int mc_compute_pdf(int scaleInv, float window, int numSamples, const int* dNumSamples, int numNeighbors,
                    const int* dNumNeighbors, float radius, const float* pts, const int* batchIds,
@@ -127,6 +135,16 @@ int mc_spatial_conv(int avg, int scaleInv, int numNeighbors, const int* dNumNeig
                     const float* samples, const int* startIdx, const int* pairs, const float* aabbMin,
                     const float* aabbMax, const float* W1, const float* b1, const float* W2, const float* b2,
                     const float* Wout, const float* bout, float* workspace, float* outFeatures, void* stream);
+
+/* Dense glue between the convolutions (TensorFlow ops in the reference: utils/MCNetworkUtils.py:20-142).
+ * mc_scale_shift_act: y = act(x * scale + shift) -- inference batch norm (+ ReLU), statistics folded by the caller.
+ * mc_dense_layer:     y = act2((act1(x * s1 + t1) @ W + bias) * s2 + t2), W [K, N] row-major; s1/t1, bias, s2/t2 may
+ *                     be NULL -- conv_1x1 and the layers of MLP_1_hidden / MLP_2_hidden, one launch per layer. */
+int mc_scale_shift_act(int numRows, const int* dNumRows, int numCols, const float* x, const float* scale,
+                       const float* shift, int relu, float* y, void* stream);
+int mc_dense_layer(int numRows, const int* dNumRows, int K, int N, const float* x, const float* s1, const float* t1,
+                   int relu1, const float* W, const float* bias, const float* s2, const float* t2, int relu2,
+                   float* y, void* stream);
 
 #ifdef __cplusplus
 }

@@ -179,13 +179,13 @@ def find_neighbors(inPts, inBatchIds, inPts2, cellIndexs, aabbMin, aabbMax, radi
     _check_aabb(aabbMin, aabbMax, batchSize, "FindNeighborsOp")
     bids = inBatchIds.reshape(-1)
     md = _cnt(inPts)
+    if _rt.mode() == "planned":  # capacity-sized pair list, live K stays on the device: one fused launch
+        plan = _rt.current_plan()
+        start, pairs, k_dev = ops.find_neighbors_fused(inPts, bids, inPts2, cellIndexs, aabbMin, aabbMax, radius,
+                                                       scaleInv, plan.next_capacity(), md, plan.overflow)
+        return _tag(start.reshape(-1, 1), md), _tag(pairs, k_dev)
     start, ws, k_dev = ops.find_neighbors_count(inPts, bids, inPts2, cellIndexs, aabbMin, aabbMax, radius, scaleInv,
                                                 md)
-    if _rt.mode() == "planned":  # capacity-sized pair list, live K stays on the device
-        plan = _rt.current_plan()
-        pairs = ops.find_neighbors_pack(inPts, bids, inPts2, cellIndexs, aabbMin, aabbMax, radius, scaleInv, start,
-                                        ws, plan.next_capacity(), md, plan.overflow)
-        return _tag(start.reshape(-1, 1), md), _tag(pairs, k_dev)
     K = int(k_dev.item())  # the one host sync of this op (the reference has the same one)
     if _rt.mode() == "record":
         _rt.current_plan().sizes.append(K)

@@ -40,6 +40,8 @@ SIGNATURES = {
                                          _ptr, _ptr, _ptr, _ptr]),
     "mc_find_neighbors_pack": (_c_int, [_c_int, _c_int, _ptr, _c_int, _c_float, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr,
                                         _ptr, _ptr, _ptr, _c_int, _ptr, _ptr]),
+    "mc_find_neighbors_fused": (_c_int, [_c_int, _c_int, _ptr, _c_int, _c_float, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr,
+                                         _ptr, _ptr, _ptr, _c_int, _ptr, _ptr, _ptr]),
     "mc_compute_pdf": (_c_int, [_c_int, _c_float, _c_int, _ptr, _c_int, _ptr, _c_float, _ptr, _ptr, _ptr, _ptr, _ptr,
                                 _ptr, _ptr, _ptr]),
     "mc_poisson_workspace_ints": (_c_ll, [_c_int, _c_int]),
@@ -49,6 +51,9 @@ SIGNATURES = {
     "mc_spatial_conv_workspace_floats": (_c_ll, [_c_int, _c_int, _c_int, _c_int]),
     "mc_spatial_conv": (_c_int, [_c_int, _c_int, _c_int, _ptr, _c_int, _c_int, _c_int, _ptr, _c_int, _c_float] +
                         [_ptr] * 18),
+    "mc_scale_shift_act": (_c_int, [_c_int, _ptr, _c_int, _ptr, _ptr, _ptr, _c_int, _ptr, _ptr]),
+    "mc_dense_layer": (_c_int, [_c_int, _ptr, _c_int, _c_int, _ptr, _ptr, _ptr, _c_int, _ptr, _ptr, _ptr, _ptr, _c_int,
+                                _ptr, _ptr]),
 }
 
 

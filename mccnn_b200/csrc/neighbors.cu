@@ -9,6 +9,7 @@
 // the float-exact one in common.cuh.  The total stays on the device (dNumNeighbors); the caller decides whether to
 // read it (exact-shape API) or to keep going with a capacity-sized pair buffer (sync-free pipeline).
 #include "common.cuh"
+#include "lookback.cuh"
 #include "scan.cuh"
 
 namespace mc {
@@ -76,12 +77,195 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32)
     if (!FILL && lane == 0) start[i] = count;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Fused count + scan + fill for the sync-free pipeline (the pair capacity is known up front): ONE launch.
+// A CTA owns 32 consecutive samples (4 per warp).  Sweep 1 evaluates every candidate once and caches the hit ballots
+// of the rounds that had hits in shared memory; the 32 counts are scanned in the CTA, the CTA total goes through the
+// decoupled look-back (lookback.cuh) to obtain the CTA's offset in the global pair list, and the cached ballots are
+// replayed into ordered (j, i) writes -- distances are computed once, no second kernel, no separate scan kernels.
+constexpr int kFusedPerWarp = 4;
+constexpr int kFusedPerCta = kWarpsPerCta * kFusedPerWarp;  // 32 samples per CTA
+constexpr int kFusedRounds = 64;                            // cached hit rounds per sample (else: re-sweep)
+static_assert(kFusedPerCta == 32, "the CTA scan of the per-sample counts uses one warp");
+
+struct FusedShared {
+    int2 rounds[kFusedPerCta][kFusedRounds];  // (first candidate of the round, hit mask)
+    int count[kFusedPerCta];
+    int nRounds[kFusedPerCta];
+    int offset[kFusedPerCta];
+    int cta, base;
+};
+
+// one sweep over the 27 cells of sample i; WRITE: emit pairs at `base` instead of caching
+template <bool WRITE>
+__device__ __forceinline__ void sweep_sample(int i, bool scaleInv, int n, float radius,
+                                             const float* __restrict__ samples, const int* __restrict__ sbids,
+                                             const float* __restrict__ pts2, const int2* __restrict__ cellIdx,
+                                             const float* __restrict__ mn, const float* __restrict__ mx, int lane,
+                                             int2* roundsOut, int& outCount, int& outRounds, int base,
+                                             int2* __restrict__ pairs, int capK, int* __restrict__ dOverflow) {
+    const int b = sbids[i];
+    const CloudFrame f = cloud_frame(mn, mx, b, n, radius, scaleInv);
+    const float sx = samples[(size_t)i * 3], sy = samples[(size_t)i * 3 + 1], sz = samples[(size_t)i * 3 + 2];
+    int cx, cy, cz;
+    cell_of(f, sx, sy, sz, n, cx, cy, cz);
+    const float thr = exact_radius_threshold(f.radius);
+    int lo = 0, hi = 0;
+    if (lane < 27) {
+        int x = cx + kOffsNeigh[lane][0], y = cy + kOffsNeigh[lane][1], z = cz + kOffsNeigh[lane][2];
+        if (x >= 0 && x < n && y >= 0 && y < n && z >= 0 && z < n) {
+            int2 c = cellIdx[(((size_t)b * n + x) * n + y) * n + z];
+            lo = c.x;
+            hi = c.y;
+        }
+    }
+    unsigned nonEmpty = __ballot_sync(MC_FULL_MASK, hi > lo);
+    const unsigned ltMask = (1u << lane) - 1u;
+    int count = 0, nr = 0;
+    while (nonEmpty) {
+        const int o = __ffs(nonEmpty) - 1;
+        nonEmpty &= nonEmpty - 1;
+        const int clo = __shfl_sync(MC_FULL_MASK, lo, o), chi = __shfl_sync(MC_FULL_MASK, hi, o);
+        for (int j0 = clo; j0 < chi; j0 += 32) {
+            const int j = j0 + lane;
+            bool in = false;
+            if (j < chi)
+                in = dist2_ref(sx, sy, sz, pts2[(size_t)j * 3], pts2[(size_t)j * 3 + 1], pts2[(size_t)j * 3 + 2]) <= thr;
+            const unsigned hit = __ballot_sync(MC_FULL_MASK, in);
+            if (hit) {
+                if (WRITE) {
+                    if (in) {
+                        const int slot = base + count + __popc(hit & ltMask);
+                        if (slot < capK)
+                            pairs[slot] = make_int2(j, i);
+                        else if (dOverflow != nullptr)
+                            *dOverflow = 1;
+                    }
+                } else if (nr < kFusedRounds && lane == 0) {
+                    roundsOut[nr] = make_int2(j0, (int)hit);
+                }
+                ++nr;
+                count += __popc(hit);
+            }
+        }
+    }
+    outCount = count;
+    outRounds = nr;
+}
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+    neighbors_fused_kernel(bool scaleInv, const int* __restrict__ dM, int capM, int n, float radius,
+                           const float* __restrict__ samples, const int* __restrict__ sbids,
+                           const float* __restrict__ pts2, const int2* __restrict__ cellIdx,
+                           const float* __restrict__ mn, const float* __restrict__ mx, unsigned long long* desc,
+                           int numCtas, int* __restrict__ start, int2* __restrict__ pairs, int capK,
+                           int* __restrict__ dNumNeighbors, int* __restrict__ dOverflow) {
+    __shared__ FusedShared sh;
+    const int M = live_count(dM, capM);
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) sh.cta = lookback_ticket(desc);
+    __syncthreads();
+    const int cta = sh.cta;
+    const int first = cta * kFusedPerCta + warp * kFusedPerWarp;
+
+    // sweep 1: count + cache the hit ballots
+    for (int s = 0; s < kFusedPerWarp; ++s) {
+        const int slot = warp * kFusedPerWarp + s;
+        const int i = first + s;
+        int cnt = 0, nr = 0;
+        if (i < M)
+            sweep_sample<false>(i, scaleInv, n, radius, samples, sbids, pts2, cellIdx, mn, mx, lane, sh.rounds[slot], cnt,
+                                nr, 0, nullptr, 0, nullptr);
+        if (lane == 0) {
+            sh.count[slot] = cnt;
+            sh.nRounds[slot] = nr;
+        }
+    }
+    __syncthreads();
+
+    // CTA scan of the 32 counts + look-back across CTAs
+    if (warp == 0) {
+        const int c = sh.count[lane];
+        const int inc = warp_inclusive_scan(c);
+        sh.offset[lane] = inc - c;
+        const int total = __shfl_sync(MC_FULL_MASK, inc, 31);
+        const int base = lookback_exclusive_prefix(desc, cta, total);
+        if (lane == 0) {
+            sh.base = base;
+            if (cta == numCtas - 1) *dNumNeighbors = base + total;
+        }
+    }
+    __syncthreads();
+
+    // replay: ordered writes from the cached ballots
+    const unsigned ltMask = (1u << lane) - 1u;
+    for (int s = 0; s < kFusedPerWarp; ++s) {
+        const int slot = warp * kFusedPerWarp + s;
+        const int i = first + s;
+        if (i >= M) break;
+        const int base = sh.base + sh.offset[slot];
+        if (lane == 0) start[i] = base;
+        const int nr = sh.nRounds[slot];
+        if (nr <= kFusedRounds) {
+            int written = 0;
+            for (int r = 0; r < nr; ++r) {
+                const int2 rd = sh.rounds[slot][r];
+                const unsigned hit = (unsigned)rd.y;
+                if (hit & (1u << lane)) {
+                    const int dst = base + written + __popc(hit & ltMask);
+                    if (dst < capK)
+                        pairs[dst] = make_int2(rd.x + lane, i);
+                    else if (dOverflow != nullptr)
+                        *dOverflow = 1;
+                }
+                written += __popc(hit);
+            }
+        } else {  // more hit rounds than the cache holds: sweep again, writing
+            int cnt, nr2;
+            sweep_sample<true>(i, scaleInv, n, radius, samples, sbids, pts2, cellIdx, mn, mx, lane, nullptr, cnt, nr2, base,
+                               pairs, capK, dOverflow);
+        }
+    }
+}
+
 }  // namespace
 }  // namespace mc
 
 using namespace mc;
 
-extern "C" long long mc_find_neighbors_workspace_ints(int numSamples) { return scan_num_tiles(numSamples) + 8; }
+extern "C" long long mc_find_neighbors_workspace_ints(int numSamples) {
+    long long tiles = scan_num_tiles(numSamples);
+    long long fused = 2LL * (cdiv(numSamples > 0 ? numSamples : 1, kFusedPerCta) + 2);  // look-back descriptors
+    return (tiles > fused ? tiles : fused) + 8;
+}
+
+// countNeighborsCPU + packNeighborsCPU (tf_ops/find_neighbors.cu:268-371) in ONE launch, for callers that provide a
+// pair capacity up front (sync-free pipeline).  startIdx receives the final start indices, *dNumNeighbors the total;
+// pairs past capacityPairs are dropped and *dOverflow is set.  workspace: mc_find_neighbors_workspace_ints, 8-byte
+// aligned.
+extern "C" int mc_find_neighbors_fused(int scaleInv, int numSamples, const int* dNumSamples, int numCells,
+                                       float radius, const float* samples, const int* sampleBatchIds,
+                                       const float* pts2, const int* cellIdx, const float* aabbMin,
+                                       const float* aabbMax, int* startIdx, int* workspace, int* pairs,
+                                       int capacityPairs, int* dNumNeighbors, int* dOverflow, void* stream) {
+    MC_REQUIRE(radius > 0.0f, "mc_find_neighbors: radius must be positive");
+    MC_REQUIRE(numCells > 0, "mc_find_neighbors: cell count must be positive");
+    MC_REQUIRE(dNumNeighbors != nullptr, "mc_find_neighbors_fused: dNumNeighbors required");
+    MC_REQUIRE(((uintptr_t)workspace) % 8 == 0, "mc_find_neighbors_fused: workspace must be 8-byte aligned");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (numSamples <= 0) {
+        cudaMemsetAsync(dNumNeighbors, 0, sizeof(int), s);
+        return check_launch("mc_find_neighbors_fused");
+    }
+    const int ctas = cdiv(numSamples, kFusedPerCta);
+    unsigned long long* desc = reinterpret_cast<unsigned long long*>(workspace);
+    cudaMemsetAsync(desc, 0, sizeof(unsigned long long) * (size_t)(ctas + 1), s);
+    neighbors_fused_kernel<<<ctas, kWarpsPerCta * 32, 0, s>>>(
+        scaleInv != 0, dNumSamples, numSamples, numCells, radius, samples, sampleBatchIds, pts2,
+        reinterpret_cast<const int2*>(cellIdx), aabbMin, aabbMax, desc, ctas, startIdx,
+        reinterpret_cast<int2*>(pairs), capacityPairs, dNumNeighbors, dOverflow);
+    return check_launch("mc_find_neighbors_fused");
+}
 
 // countNeighborsCPU, tf_ops/find_neighbors.cu:268-317 -- without the cudaMalloc / D2H: the total lands in
 // *dNumNeighbors (device).  startIdx receives the tile-local exclusive prefix; mc_find_neighbors_pack finalises it.

@@ -173,6 +173,22 @@ def find_neighbors_pack(samples, sbids, pts2, cell_idx, aabb_min, aabb_max, radi
     return pairs
 
 
+def find_neighbors_fused(samples, sbids, pts2, cell_idx, aabb_min, aabb_max, radius, scale_inv, capacity, m_dev=None,
+                         overflow=None):
+    """Count + scan + fill in one launch.  Returns (start[M], pairs[capacity, 2], k_dev)."""
+    samples, sbids, pts2, cell_idx = _f(samples), _i(sbids), _f(pts2), _i(cell_idx)
+    dev = _dev(samples)
+    M = samples.shape[0]
+    start = torch.empty((M,), dtype=_i32, device=dev)
+    pairs = torch.empty((capacity, 2), dtype=_i32, device=dev)
+    k_dev = torch.empty((1,), dtype=_i32, device=dev)
+    ws = torch.empty((lib.mc_find_neighbors_workspace_ints(M),), dtype=_i32, device=dev)
+    check(lib.mc_find_neighbors_fused(int(scale_inv), M, _p(m_dev), cell_idx.shape[1], float(radius), _p(samples),
+                                      _p(sbids), _p(pts2), _p(cell_idx), _p(aabb_min), _p(aabb_max), _p(start), _p(ws),
+                                      _p(pairs), capacity, _p(k_dev), _p(overflow), _stream()))
+    return start, pairs, k_dev
+
+
 def compute_pdf(pts, bids, aabb_min, aabb_max, start, pairs, window, radius, scale_inv, m_dev=None, k_dev=None):
     pts, bids, start, pairs = _f(pts), _i(bids), _i(start), _i(pairs)
     dev = _dev(pts)
@@ -226,3 +242,27 @@ def spatial_conv(pts, feats, bids, pdfs, samples, start, pairs, aabb_min, aabb_m
                               _p(pairs), _p(aabb_min), _p(aabb_max), _p(w1), _p(b1), _p(w2), _p(b2), _p(wout),
                               _p(bout), _p(ws), _p(out), _stream()))
     return out
+
+
+def scale_shift_act(x, scale, shift, relu, n_dev=None):
+    """y = act(x * scale + shift) per column (inference batch norm + ReLU), live rows only."""
+    x, scale, shift = _f(x), _f(scale), _f(shift)
+    y = torch.empty_like(x)
+    check(lib.mc_scale_shift_act(x.shape[0], _p(n_dev), x.shape[1], _p(x), _p(scale), _p(shift), int(relu), _p(y),
+                                 _stream()))
+    return y
+
+
+def dense_layer(x, w, bias=None, pre=None, pre_relu=False, post=None, post_relu=False, n_dev=None):
+    """y = act2((act1(x * pre[0] + pre[1]) @ w + bias) * post[0] + post[1]); w [K, N] row-major."""
+    x, w = _f(x), _f(w)
+    K, N = w.shape
+    if x.shape[1] != K:
+        raise ValueError("dense_layer: input has %d columns, weights expect %d" % (x.shape[1], K))
+    y = torch.empty((x.shape[0], N), dtype=_f32, device=_dev(x))
+    s1, t1 = (None, None) if pre is None else (_f(pre[0]), _f(pre[1]))
+    s2, t2 = (None, None) if post is None else (_f(post[0]), _f(post[1]))
+    b = None if bias is None else _f(bias)
+    check(lib.mc_dense_layer(x.shape[0], _p(n_dev), K, N, _p(x), _p(s1), _p(t1), int(pre_relu), _p(w), _p(b), _p(s2),
+                             _p(t2), int(post_relu), _p(y), _stream()))
+    return y

@@ -254,3 +254,36 @@ def test_edge_cases(env):
         M.compute_aabb(T(pts), T(bids), 0, True)
     with pytest.raises(ValueError):
         M.sort_features(T(feats), T(np.zeros((3,), np.int32)))
+
+
+def test_dense_glue_matches_torch(env):
+    """mc_scale_shift_act / mc_dense_layer (csrc/dense.cu) against the plain PyTorch fp32 formulation of the
+    reference's TensorFlow glue (utils/MCNetworkUtils.py:20-142), 1e-5 relative."""
+    e = env
+    torch, T, A = e["torch"], e["T"], e["A"]
+    from mccnn_b200 import ops
+    rng = np.random.default_rng(3)
+    for rows, K, N in ((5400, 64, 128), (387, 128, 256), (32, 256, 128), (32, 64, 40), (7, 5, 3), (100, 33, 70)):
+        x = T(rng.normal(size=(rows, K)).astype(np.float32))
+        w = T((rng.normal(size=(K, N)) / np.sqrt(K)).astype(np.float32))
+        b = T(rng.normal(size=(N,)).astype(np.float32) * 0.1)
+        s1, t1 = T(rng.uniform(0.5, 1.5, K).astype(np.float32)), T(rng.normal(size=K).astype(np.float32) * 0.1)
+        s2, t2 = T(rng.uniform(0.5, 1.5, N).astype(np.float32)), T(rng.normal(size=N).astype(np.float32) * 0.1)
+        want = torch.relu((torch.relu(x.double() * s1.double() + t1.double()) @ w.double() + b.double()) * s2.double()
+                          + t2.double())
+        got = ops.dense_layer(x, w, b, pre=(s1, t1), pre_relu=True, post=(s2, t2), post_relu=True)
+        scale = (torch.relu(x.double() * s1.double() + t1.double()).abs() @ w.double().abs() + b.double().abs()) \
+            * s2.double() + t2.double().abs()
+        assert float(((got.double() - want).abs() / scale).max()) <= RTOL
+        plain = ops.dense_layer(x, w)
+        ref = x.double() @ w.double()
+        assert float(((plain.double() - ref).abs() / (x.double().abs() @ w.double().abs() + 1e-30)).max()) <= RTOL
+        y = ops.scale_shift_act(x, s1, t1, True)
+        assert float((y - torch.relu(torch.addcmul(t1, x, s1))).abs().max()) <= 1e-6
+    # live row count: rows past the count are not touched
+    x = T(rng.normal(size=(64, 16)).astype(np.float32))
+    w = T(rng.normal(size=(16, 8)).astype(np.float32))
+    cnt = torch.tensor([10], dtype=torch.int32, device=e["dev"])
+    full = ops.dense_layer(x, w)
+    part = ops.dense_layer(x, w, n_dev=cnt)
+    assert torch.equal(part[:10], full[:10])
