@@ -139,12 +139,13 @@ int mc_spatial_conv(int avg, int scaleInv, int numNeighbors, const int* dNumNeig
 /* Dense glue between the convolutions (TensorFlow ops in the reference: utils/MCNetworkUtils.py:20-142).
  * mc_scale_shift_act: y = act(x * scale + shift) -- inference batch norm (+ ReLU), statistics folded by the caller.
  * mc_dense_layer:     y = act2((act1(x * s1 + t1) @ W + bias) * s2 + t2), W [K, N] row-major; s1/t1, bias, s2/t2 may
- *                     be NULL -- conv_1x1 and the layers of MLP_1_hidden / MLP_2_hidden, one launch per layer. */
+ *                     be NULL -- conv_1x1 and the layers of MLP_1_hidden / MLP_2_hidden, one launch per layer.
+ *                     numRowsHint (<= 0: unknown): host estimate of the live row count, selects the kernel variant. */
 int mc_scale_shift_act(int numRows, const int* dNumRows, int numCols, const float* x, const float* scale,
                        const float* shift, int relu, float* y, void* stream);
-int mc_dense_layer(int numRows, const int* dNumRows, int K, int N, const float* x, const float* s1, const float* t1,
-                   int relu1, const float* W, const float* bias, const float* s2, const float* t2, int relu2,
-                   float* y, void* stream);
+int mc_dense_layer(int numRows, const int* dNumRows, int numRowsHint, int K, int N, const float* x, const float* s1,
+                   const float* t1, int relu1, const float* W, const float* bias, const float* s2, const float* t2,
+                   int relu2, float* y, void* stream);
 
 #ifdef __cplusplus
 }

@@ -226,7 +226,8 @@ def poisson_sampling(inPts, inBatchIds, cellIndexs, aabbMin, aabbMax, radius, ba
         plan = _rt.current_plan()
         p, b, idx, m_dev = ops.poisson_sampling(inPts, inBatchIds.reshape(-1), cellIndexs, aabbMin, aabbMax, radius,
                                                 batchSize, scaleInv, nd, plan.next_capacity(), plan.overflow)
-        return _tag(p, m_dev), _tag(b.reshape(-1, 1), m_dev), _tag(idx, m_dev)
+        h = plan.last_recorded
+        return _tag(p, m_dev, h), _tag(b.reshape(-1, 1), m_dev, h), _tag(idx, m_dev, h)
     p, b, idx, m_dev = ops.poisson_sampling(inPts, inBatchIds.reshape(-1), cellIndexs, aabbMin, aabbMax, radius,
                                             batchSize, scaleInv, nd)
     M = int(m_dev.item())  # host sync, as poisson_sampling.cu:222
@@ -290,4 +291,4 @@ def spatial_conv(inPts, inFeatures, inBatchIds, inPDFs, inSamplePts, neighStartI
                            neighStartIndexs.reshape(-1), packedNeighs, aabbMin, aabbMax, weights1, biases1, weights2,
                            biases2, weightsOut, biasesOut, numOutFeatures, combin, radius, scaleInv, avg, md,
                            _cnt(packedNeighs))
-    return _tag(out, md)
+    return _tag(out, md, _rt.hint_of(inSamplePts))

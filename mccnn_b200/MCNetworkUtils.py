@@ -12,7 +12,7 @@ import torch
 
 from . import ops
 from . import variables as _vars
-from .runtime import count_of as _cnt, tag as _tag
+from .runtime import count_of as _cnt, hint_of as _hint, tag as _tag
 
 BN_EPSILON = 1e-3  # tf.layers.batch_normalization default
 
@@ -42,10 +42,19 @@ def _bn_affine(c, training, name, vs):
     return hit[1], hit[2]
 
 
+def _dense(x, w, b, **kw):
+    nd, h = _cnt(x), _hint(x)
+    return _tag(ops.dense_layer(x, w, b, n_dev=nd, rows_hint=h, **kw), nd, h)
+
+
+def _affine_act(x, scale, shift, relu):
+    nd = _cnt(x)
+    return _tag(ops.scale_shift_act(x, scale, shift, relu, nd), nd, _hint(x))
+
+
 def batch_normalization(inputs, training, name, store=None):
     scale, shift = _bn_affine(inputs.shape[1], training, name, _store(store))
-    nd = _cnt(inputs)
-    return _tag(ops.scale_shift_act(inputs, scale, shift, False, nd), nd)
+    return _affine_act(inputs, scale, shift, False)
 
 
 def MLP_2_hidden(features, numInputFeatures, hidden1_units, hidden2_units, numOutFeatures, layerName, keepProb,
@@ -53,52 +62,46 @@ def MLP_2_hidden(features, numInputFeatures, hidden1_units, hidden2_units, numOu
     """utils/MCNetworkUtils.py:20-69 (dropout is the identity at inference: keepProb = 1).  Three launches: the
     initial batch norm is the prologue of layer 1, each hidden batch norm + ReLU the epilogue of its layer."""
     vs = _store(store)
-    nd = _cnt(features)
     pre = _bn_affine(numInputFeatures, isTraining, layerName + "_BN_Init", vs) if useInitBN else None
     w1 = vs.get_variable(layerName + '_weights1', [numInputFeatures, hidden1_units], "glorot")
     vs.add_to_collection('weight_decay_loss', w1)
     b1 = vs.get_variable(layerName + '_biases1', [hidden1_units], "zeros")
-    h1 = ops.dense_layer(features, w1, b1, pre=pre, post=_bn_affine(hidden1_units, isTraining, layerName + "_BN_h1", vs),
-                         post_relu=True, n_dev=nd)
+    h1 = _dense(features, w1, b1, pre=pre, post=_bn_affine(hidden1_units, isTraining, layerName + "_BN_h1", vs),
+                post_relu=True)
     w2 = vs.get_variable(layerName + '_weights2', [hidden1_units, hidden2_units], "glorot")
     vs.add_to_collection('weight_decay_loss', w2)
     b2 = vs.get_variable(layerName + '_biases2', [hidden2_units], "zeros")
-    h2 = ops.dense_layer(h1, w2, b2, post=_bn_affine(hidden2_units, isTraining, layerName + "_BN_h2", vs),
-                         post_relu=True, n_dev=nd)
+    h2 = _dense(h1, w2, b2, post=_bn_affine(hidden2_units, isTraining, layerName + "_BN_h2", vs), post_relu=True)
     w3 = vs.get_variable(layerName + '_weights3', [hidden2_units, numOutFeatures], "glorot")
     vs.add_to_collection('weight_decay_loss', w3)
     b3 = vs.get_variable(layerName + '_biases3', [numOutFeatures], "zeros")
-    return _tag(ops.dense_layer(h2, w3, b3, n_dev=nd), nd)
+    return _dense(h2, w3, b3)
 
 
 def MLP_1_hidden(features, numInputFeatures, hidden_units, numOutFeatures, layerName, keepProb, isTraining,
                  useDropOut=False, store=None):
     """utils/MCNetworkUtils.py:71-107."""
     vs = _store(store)
-    nd = _cnt(features)
     w1 = vs.get_variable(layerName + '_weights1', [numInputFeatures, hidden_units], "glorot")
     vs.add_to_collection('weight_decay_loss', w1)
     b1 = vs.get_variable(layerName + '_biases1', [hidden_units], "zeros")
-    h = ops.dense_layer(features, w1, b1, post=_bn_affine(hidden_units, isTraining, layerName + "_BN_h", vs),
-                        post_relu=True, n_dev=nd)
+    h = _dense(features, w1, b1, post=_bn_affine(hidden_units, isTraining, layerName + "_BN_h", vs), post_relu=True)
     w2 = vs.get_variable(layerName + '_weights2', [hidden_units, numOutFeatures], "glorot")
     vs.add_to_collection('weight_decay_loss', w2)
     b2 = vs.get_variable(layerName + '_biases2', [numOutFeatures], "zeros")
-    return _tag(ops.dense_layer(h, w2, b2, n_dev=nd), nd)
+    return _dense(h, w2, b2)
 
 
 def conv_1x1(layerName, inputs, numInputs, numOutFeatures, store=None):
     """utils/MCNetworkUtils.py:109-126."""
     vs = _store(store)
-    nd = _cnt(inputs)
     w = vs.get_variable(layerName + '_weights', [numInputs, numOutFeatures], "glorot")
     vs.add_to_collection('weight_decay_loss', w)
     b = vs.get_variable(layerName + '_biases', [numOutFeatures], "zeros")
-    return _tag(ops.dense_layer(inputs, w, b, n_dev=nd), nd)
+    return _dense(inputs, w, b)
 
 
 def batch_norm_RELU_drop_out(layerName, inFeatures, isTraining, usedDropOut, keepProb, store=None):
     """utils/MCNetworkUtils.py:128-142 (dropout is the identity at inference)."""
     scale, shift = _bn_affine(inFeatures.shape[1], isTraining, layerName + "_BN", _store(store))
-    nd = _cnt(inFeatures)
-    return _tag(ops.scale_shift_act(inFeatures, scale, shift, True, nd), nd)
+    return _affine_act(inFeatures, scale, shift, True)

@@ -52,8 +52,8 @@ SIGNATURES = {
     "mc_spatial_conv": (_c_int, [_c_int, _c_int, _c_int, _ptr, _c_int, _c_int, _c_int, _ptr, _c_int, _c_float] +
                         [_ptr] * 18),
     "mc_scale_shift_act": (_c_int, [_c_int, _ptr, _c_int, _ptr, _ptr, _ptr, _c_int, _ptr, _ptr]),
-    "mc_dense_layer": (_c_int, [_c_int, _ptr, _c_int, _c_int, _ptr, _ptr, _ptr, _c_int, _ptr, _ptr, _ptr, _ptr, _c_int,
-                                _ptr, _ptr]),
+    "mc_dense_layer": (_c_int, [_c_int, _ptr, _c_int, _c_int, _c_int, _ptr, _ptr, _ptr, _c_int, _ptr, _ptr, _ptr, _ptr,
+                                _c_int, _ptr, _ptr]),
 }
 
 

@@ -1,20 +1,24 @@
 // dense.cu -- the dense glue between Monte-Carlo convolutions (utils/MCNetworkUtils.py:20-142 in the reference, where
 // it is TensorFlow: tf.layers.batch_normalization (inference), tf.nn.relu, tf.matmul + bias).
 //
-// Two kernels:
 //   scale_shift_act   y = act(x * scale + shift)                 batch_norm_RELU_drop_out at inference
 //   dense_layer       y = act2( (act1(x * s1 + t1) @ W + b) * s2 + t2 )
 //                     conv_1x1 and each layer of MLP_1_hidden / MLP_2_hidden with the surrounding inference
 //                     batch-norms folded into per-column scale / shift vectors (any of s1/t1/s2/t2/b may be NULL)
-// The matrices are tiny (<= 512 x 512) and the row counts small (tens to thousands), so this is a plain register-
-// tiled FP32 FFMA GEMM (32 x 64 output tile per CTA, K staged through shared memory in chunks of 32); what matters is
-// ONE launch per layer instead of the 2-6 library launches of the eager formulation.  FP32 accumulate in k order.
+// The matrices are tiny (<= 512 x 512) and the row counts small, so the layers are LATENCY bound, not FLOP bound; two
+// FP32 FFMA kernels cover the two regimes with ONE launch per layer (instead of 2-6 library launches):
+//   * dense_rows_kernel  (few rows, e.g. the 32-row classification head): one CTA per row, the 256 threads split
+//     into (column, K-slice) pairs so that the K loop is short, W is read straight from L2 with coalesced loads, the
+//     slices are reduced through shared memory;
+//   * dense_tiles_kernel (many rows): 32 x 64 output tile per CTA, K staged through shared memory in chunks of 32
+//     with the next chunk prefetched into registers while the current one is multiplied.
 #include "common.cuh"
 
 namespace mc {
 namespace {
 
 constexpr int kDnBM = 32, kDnBN = 64, kDnBK = 32, kDnThreads = 256;
+constexpr int kRowsMaxK = 1024;  // dense_rows_kernel keeps one activated input row in shared memory
 
 __global__ void __launch_bounds__(256) scale_shift_act_kernel(const int* __restrict__ dRows, int capRows, int cols,
                                                               const float* __restrict__ x,
@@ -31,34 +35,107 @@ __global__ void __launch_bounds__(256) scale_shift_act_kernel(const int* __restr
     }
 }
 
+__device__ __forceinline__ float epilogue(float v, int c, const float* __restrict__ bias, const float* __restrict__ s2,
+                                          const float* __restrict__ t2, int relu2) {
+    if (bias != nullptr) v += bias[c];
+    if (s2 != nullptr) v = fmaf(v, s2[c], t2[c]);
+    return relu2 ? fmaxf(v, 0.0f) : v;
+}
+
+// one CTA per row; threads = (column c, K-slice s)
 __global__ void __launch_bounds__(kDnThreads)
-    dense_layer_kernel(const int* __restrict__ dRows, int capRows, int K, int N, const float* __restrict__ x,
+    dense_rows_kernel(const int* __restrict__ dRows, int capRows, int K, int N, const float* __restrict__ x,
+                      const float* __restrict__ s1, const float* __restrict__ t1, int relu1,
+                      const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ s2,
+                      const float* __restrict__ t2, int relu2, float* __restrict__ y) {
+    __shared__ float sA[kRowsMaxK];
+    __shared__ float sPart[kDnThreads];
+    const int rows = live_count(dRows, capRows);
+    const int r = blockIdx.x;
+    if (r >= rows) return;
+    for (int k = threadIdx.x; k < K; k += kDnThreads) {
+        float v = x[(size_t)r * K + k];
+        if (s1 != nullptr) v = fmaf(v, s1[k], t1[k]);
+        sA[k] = relu1 ? fmaxf(v, 0.0f) : v;
+    }
+    __syncthreads();
+    for (int c0 = 0; c0 < N; c0 += kDnThreads) {
+        const int cols = min(N - c0, kDnThreads);
+        const int slices = kDnThreads / cols;
+        const int c = threadIdx.x % cols, s = threadIdx.x / cols;
+        float acc = 0.0f;
+        if (s < slices) {
+            const int kPer = (K + slices - 1) / slices;
+            const int kBeg = s * kPer, kEnd = min(K, kBeg + kPer);
+            const float* w = W + (size_t)kBeg * N + c0 + c;
+            int k = kBeg;
+            for (; k + 8 <= kEnd; k += 8) {  // 8 independent L2 loads in flight
+                float wv[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) wv[u] = w[(size_t)u * N];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) acc = fmaf(sA[k + u], wv[u], acc);
+                w += (size_t)8 * N;
+            }
+            for (; k < kEnd; ++k) {
+                acc = fmaf(sA[k], *w, acc);
+                w += N;
+            }
+        }
+        sPart[threadIdx.x] = acc;
+        __syncthreads();
+        if (threadIdx.x < cols) {
+            float v = 0.0f;
+            for (int q = 0; q < slices; ++q) v += sPart[q * cols + threadIdx.x];  // fixed order: deterministic
+            y[(size_t)r * N + c0 + threadIdx.x] = epilogue(v, c0 + threadIdx.x, bias, s2, t2, relu2);
+        }
+        __syncthreads();
+    }
+}
+
+// 32 x 64 output tile per CTA, register-prefetched K chunks
+__global__ void __launch_bounds__(kDnThreads)
+    dense_tiles_kernel(const int* __restrict__ dRows, int capRows, int K, int N, const float* __restrict__ x,
                        const float* __restrict__ s1, const float* __restrict__ t1, int relu1,
                        const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ s2,
                        const float* __restrict__ t2, int relu2, float* __restrict__ y) {
     __shared__ float sA[kDnBM][kDnBK + 1];
-    __shared__ float sW[kDnBK][kDnBN];
+    __shared__ __align__(16) float sW[kDnBK][kDnBN];
     const int rows = live_count(dRows, capRows);
     const int row0 = blockIdx.x * kDnBM, col0 = blockIdx.y * kDnBN;
     if (row0 >= rows) return;
     const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;  // 16 x 16 threads: 4 columns x 2 rows each
-    float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-    for (int k0 = 0; k0 < K; k0 += kDnBK) {
-        for (int e = threadIdx.x; e < kDnBM * kDnBK; e += kDnThreads) {  // A tile with the input affine + activation
-            const int r = e / kDnBK, k = e % kDnBK;
+    // staging assignment: A tile 32x32 -> 4 elements per thread, W tile 32x64 -> 8 elements per thread
+    const int aR = threadIdx.x / 8, aK = (threadIdx.x % 8) * 4;   // 4 consecutive k of one row
+    const int wK = threadIdx.x / 8, wC = (threadIdx.x % 8) * 8;   // 8 consecutive columns of one k
+    float ra[4], rw[8];
+    auto fetch = [&](int k0) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int r = row0 + aR, k = k0 + aK + u;
             float v = 0.0f;
-            if (row0 + r < rows && k0 + k < K) {
-                v = x[(size_t)(row0 + r) * K + k0 + k];
-                if (s1 != nullptr) v = fmaf(v, s1[k0 + k], t1[k0 + k]);
+            if (r < rows && k < K) {
+                v = x[(size_t)r * K + k];
+                if (s1 != nullptr) v = fmaf(v, s1[k], t1[k]);
                 if (relu1) v = fmaxf(v, 0.0f);
             }
-            sA[r][k] = v;
+            ra[u] = v;
         }
-        for (int e = threadIdx.x; e < kDnBK * kDnBN; e += kDnThreads) {
-            const int k = e / kDnBN, c = e % kDnBN;
-            sW[k][c] = (k0 + k < K && col0 + c < N) ? W[(size_t)(k0 + k) * N + col0 + c] : 0.0f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int k = k0 + wK, c = col0 + wC + u;
+            rw[u] = (k < K && c < N) ? W[(size_t)k * N + c] : 0.0f;
         }
+    };
+    float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    fetch(0);
+    for (int k0 = 0; k0 < K; k0 += kDnBK) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) sA[aR][aK + u] = ra[u];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) sW[wK][wC + u] = rw[u];
         __syncthreads();
+        if (k0 + kDnBK < K) fetch(k0 + kDnBK);  // next chunk's global loads overlap this chunk's FMAs
 #pragma unroll 8
         for (int k = 0; k < kDnBK; ++k) {
             const float a0 = sA[ty * 2][k], a1 = sA[ty * 2 + 1][k];
@@ -81,12 +158,7 @@ __global__ void __launch_bounds__(kDnThreads)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int c = col0 + tx * 4 + j;
-            if (c >= N) continue;
-            float v = acc[i][j];
-            if (bias != nullptr) v += bias[c];
-            if (s2 != nullptr) v = fmaf(v, s2[c], t2[c]);
-            if (relu2) v = fmaxf(v, 0.0f);
-            y[(size_t)r * N + c] = v;
+            if (c < N) y[(size_t)r * N + c] = epilogue(acc[i][j], c, bias, s2, t2, relu2);
         }
     }
 }
@@ -110,16 +182,24 @@ extern "C" int mc_scale_shift_act(int numRows, const int* dNumRows, int numCols,
 }
 
 // y = act2((act1(x * s1 + t1) @ W + bias) * s2 + t2); x [rows, K], W [K, N] row-major (the reference's weight layout,
-// utils/MCNetworkUtils.py:44,123), y [rows, N].  s1/t1, bias, s2/t2 optional (NULL).
-extern "C" int mc_dense_layer(int numRows, const int* dNumRows, int K, int N, const float* x, const float* s1,
-                              const float* t1, int relu1, const float* W, const float* bias, const float* s2,
-                              const float* t2, int relu2, float* y, void* stream) {
+// utils/MCNetworkUtils.py:44,123), y [rows, N].  s1/t1, bias, s2/t2 optional (NULL).  `numRowsHint` (<= 0: unknown)
+// is the caller's estimate of the LIVE row count; it only selects the kernel variant.
+extern "C" int mc_dense_layer(int numRows, const int* dNumRows, int numRowsHint, int K, int N, const float* x,
+                              const float* s1, const float* t1, int relu1, const float* W, const float* bias,
+                              const float* s2, const float* t2, int relu2, float* y, void* stream) {
     MC_REQUIRE(K > 0 && N > 0, "mc_dense_layer: layer sizes must be positive");
     MC_REQUIRE((s1 == nullptr) == (t1 == nullptr) && (s2 == nullptr) == (t2 == nullptr),
                "mc_dense_layer: scale and shift come in pairs");
     if (numRows <= 0) return 0;
-    dim3 grid(cdiv(numRows, kDnBM), cdiv(N, kDnBN));
-    dense_layer_kernel<<<grid, kDnThreads, 0, (cudaStream_t)stream>>>(dNumRows, numRows, K, N, x, s1, t1, relu1, W, bias,
-                                                                    s2, t2, relu2, y);
+    cudaStream_t s = (cudaStream_t)stream;
+    const int live = (numRowsHint > 0 && numRowsHint < numRows) ? numRowsHint : numRows;
+    if (live <= 128 && K <= kRowsMaxK) {
+        dense_rows_kernel<<<numRows, kDnThreads, 0, s>>>(dNumRows, numRows, K, N, x, s1, t1, relu1, W, bias, s2, t2,
+                                                          relu2, y);
+    } else {
+        dim3 grid(cdiv(numRows, kDnBM), cdiv(N, kDnBN));
+        dense_tiles_kernel<<<grid, kDnThreads, 0, s>>>(dNumRows, numRows, K, N, x, s1, t1, relu1, W, bias, s2, t2, relu2,
+                                                       y);
+    }
     return check_launch("mc_dense_layer");
 }

@@ -153,6 +153,9 @@ __device__ __forceinline__ void sweep_sample(int i, bool scaleInv, int n, float 
     outRounds = nr;
 }
 
+// PER_WARP samples per warp: 1 keeps the per-warp serial chain short when there are few samples (latency bound),
+// 4 keeps the look-back chain short when there are many.
+template <int PER_WARP>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
     neighbors_fused_kernel(bool scaleInv, const int* __restrict__ dM, int capM, int n, float radius,
                            const float* __restrict__ samples, const int* __restrict__ sbids,
@@ -160,13 +163,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32)
                            const float* __restrict__ mn, const float* __restrict__ mx, unsigned long long* desc,
                            int numCtas, int* __restrict__ start, int2* __restrict__ pairs, int capK,
                            int* __restrict__ dNumNeighbors, int* __restrict__ dOverflow) {
+    constexpr int kFusedPerWarp = PER_WARP;
+    constexpr int kPerCta = kWarpsPerCta * PER_WARP;
     __shared__ FusedShared sh;
     const int M = live_count(dM, capM);
     const int lane = lane_id(), warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) sh.cta = lookback_ticket(desc);
     __syncthreads();
     const int cta = sh.cta;
-    const int first = cta * kFusedPerCta + warp * kFusedPerWarp;
+    const int first = cta * kPerCta + warp * kFusedPerWarp;
 
     // sweep 1: count + cache the hit ballots
     for (int s = 0; s < kFusedPerWarp; ++s) {
@@ -185,9 +190,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32)
 
     // CTA scan of the 32 counts + look-back across CTAs
     if (warp == 0) {
-        const int c = sh.count[lane];
+        const int c = lane < kPerCta ? sh.count[lane] : 0;
         const int inc = warp_inclusive_scan(c);
-        sh.offset[lane] = inc - c;
+        if (lane < kPerCta) sh.offset[lane] = inc - c;
         const int total = __shfl_sync(MC_FULL_MASK, inc, 31);
         const int base = lookback_exclusive_prefix(desc, cta, total);
         if (lane == 0) {
@@ -235,7 +240,7 @@ using namespace mc;
 
 extern "C" long long mc_find_neighbors_workspace_ints(int numSamples) {
     long long tiles = scan_num_tiles(numSamples);
-    long long fused = 2LL * (cdiv(numSamples > 0 ? numSamples : 1, kFusedPerCta) + 2);  // look-back descriptors
+    long long fused = 2LL * (cdiv(numSamples > 0 ? numSamples : 1, kWarpsPerCta) + 2);  // look-back descriptors
     return (tiles > fused ? tiles : fused) + 8;
 }
 
@@ -257,13 +262,20 @@ extern "C" int mc_find_neighbors_fused(int scaleInv, int numSamples, const int* 
         cudaMemsetAsync(dNumNeighbors, 0, sizeof(int), s);
         return check_launch("mc_find_neighbors_fused");
     }
-    const int ctas = cdiv(numSamples, kFusedPerCta);
+    const bool few = numSamples <= 16384;
+    const int ctas = cdiv(numSamples, few ? kWarpsPerCta : kFusedPerCta);
     unsigned long long* desc = reinterpret_cast<unsigned long long*>(workspace);
     cudaMemsetAsync(desc, 0, sizeof(unsigned long long) * (size_t)(ctas + 1), s);
-    neighbors_fused_kernel<<<ctas, kWarpsPerCta * 32, 0, s>>>(
-        scaleInv != 0, dNumSamples, numSamples, numCells, radius, samples, sampleBatchIds, pts2,
-        reinterpret_cast<const int2*>(cellIdx), aabbMin, aabbMax, desc, ctas, startIdx,
-        reinterpret_cast<int2*>(pairs), capacityPairs, dNumNeighbors, dOverflow);
+    const int2* cells = reinterpret_cast<const int2*>(cellIdx);
+    int2* prs = reinterpret_cast<int2*>(pairs);
+    if (few)
+        neighbors_fused_kernel<1><<<ctas, kWarpsPerCta * 32, 0, s>>>(
+            scaleInv != 0, dNumSamples, numSamples, numCells, radius, samples, sampleBatchIds, pts2, cells, aabbMin,
+            aabbMax, desc, ctas, startIdx, prs, capacityPairs, dNumNeighbors, dOverflow);
+    else
+        neighbors_fused_kernel<kFusedPerWarp><<<ctas, kWarpsPerCta * 32, 0, s>>>(
+            scaleInv != 0, dNumSamples, numSamples, numCells, radius, samples, sampleBatchIds, pts2, cells, aabbMin,
+            aabbMax, desc, ctas, startIdx, prs, capacityPairs, dNumNeighbors, dOverflow);
     return check_launch("mc_find_neighbors_fused");
 }
 

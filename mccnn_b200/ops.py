@@ -253,7 +253,7 @@ def scale_shift_act(x, scale, shift, relu, n_dev=None):
     return y
 
 
-def dense_layer(x, w, bias=None, pre=None, pre_relu=False, post=None, post_relu=False, n_dev=None):
+def dense_layer(x, w, bias=None, pre=None, pre_relu=False, post=None, post_relu=False, n_dev=None, rows_hint=0):
     """y = act2((act1(x * pre[0] + pre[1]) @ w + bias) * post[0] + post[1]); w [K, N] row-major."""
     x, w = _f(x), _f(w)
     K, N = w.shape
@@ -263,6 +263,6 @@ def dense_layer(x, w, bias=None, pre=None, pre_relu=False, post=None, post_relu=
     s1, t1 = (None, None) if pre is None else (_f(pre[0]), _f(pre[1]))
     s2, t2 = (None, None) if post is None else (_f(post[0]), _f(post[1]))
     b = None if bias is None else _f(bias)
-    check(lib.mc_dense_layer(x.shape[0], _p(n_dev), K, N, _p(x), _p(s1), _p(t1), int(pre_relu), _p(w), _p(b), _p(s2),
+    check(lib.mc_dense_layer(x.shape[0], _p(n_dev), int(rows_hint or 0), K, N, _p(x), _p(s1), _p(t1), int(pre_relu), _p(w), _p(b), _p(s2),
                              _p(t2), int(post_relu), _p(y), _stream()))
     return y

@@ -51,6 +51,7 @@ class Plan:
         if self._cursor >= len(self.capacities):
             raise RuntimeError("mccnn_b200: the planned run issues more dynamic ops than were recorded")
         c = self.capacities[self._cursor]
+        self.last_recorded = self.sizes[self._cursor]  # live size seen when recording: a host-side hint
         self._cursor += 1
         return c
 
@@ -182,7 +183,15 @@ def count_of(t):
     return getattr(t, "_mc_count", None)
 
 
-def tag(t, count):
+def tag(t, count, hint=None):
+    """Attach the live row count (device int) and, optionally, a host-side estimate of it (the size recorded when the
+    plan was made; used only to pick kernel variants / launch shapes, never for correctness)."""
     if count is not None:
         t._mc_count = count
+    if hint is not None:
+        t._mc_hint = hint
     return t
+
+
+def hint_of(t):
+    return getattr(t, "_mc_hint", None)
