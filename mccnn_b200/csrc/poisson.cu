@@ -32,6 +32,8 @@ constexpr int kSelFlagBytes = 48 * 1024;  // per-cloud accepted flags kept in sh
 constexpr int kListCap = 128;             // accepted neighbour candidates a warp keeps in shared memory
 constexpr int kSelfOffset = 17;           // index of (0,0,0) in kOffsPool
 constexpr int kCellListCap = 8192;        // cells per cloud up to which the per-phase non-empty cell lists are built
+constexpr int kStageCells = 4096;         // cell-table rows of a cloud staged in shared memory up to this many cells
+constexpr int kStagePts = 4096;           // points of a cloud staged in shared memory up to this many points
 
 // phase (index into kOffsPool) of the offset (ox, oy, oz), indexed by (ox+1)*9 + (oy+1)*3 + (oz+1)
 __device__ __constant__ const unsigned char kPhaseOfOffset[27] = {
@@ -54,8 +56,17 @@ struct SelShared {
 };
 
 struct CloudCtx {
-    const int2* cells;
-    const float* pts;
+    const int2* cells;            // this cloud's rows of the cell table (global)
+    const int2* sCells;           // the same rows staged in shared memory, or nullptr
+    const float* pts;             // sorted points (global)
+    const float* sPts;            // this cloud's points staged in shared memory (index: sorted position - cLo), or nullptr
+    __device__ __forceinline__ int2 cell(int c) const { return sCells ? sCells[c] : cells[c]; }
+    __device__ __forceinline__ void point(int j, float& x, float& y, float& z) const {
+        const float* p = sPts ? sPts + (size_t)(j - cLo) * 3 : pts + (size_t)j * 3;
+        x = p[0];
+        y = p[1];
+        z = p[2];
+    }
     unsigned char* sFlags;        // shared-memory flags (index: sorted position - cLo) or nullptr
     unsigned char* gFlags;        // global flags (index: sorted position) when the cloud does not fit
     int cLo;
@@ -82,7 +93,7 @@ __device__ __forceinline__ void process_cell(const CloudCtx& cx, SelShared& sh, 
     if (lane < 27 && lane != kSelfOffset) {
         int qx = x + kOffsPool[lane][0], qy = y + kOffsPool[lane][1], qz = z + kOffsPool[lane][2];
         if (qx >= 0 && qx < n && qy >= 0 && qy < n && qz >= 0 && qz < n) {
-            int2 ce = cx.cells[(qx * n + qy) * n + qz];
+            int2 ce = cx.cell((qx * n + qy) * n + qz);
             nlo = ce.x;
             nhi = ce.y;
         }
@@ -99,8 +110,9 @@ __device__ __forceinline__ void process_cell(const CloudCtx& cx, SelShared& sh, 
     bool listOk = L <= kListCap;  // else: fall back to walking the cells directly (never wrong, only slow)
     if (listOk) {
         for (int t = lane; t < L; t += 32) {
-            int j = sh.listIdx[warp][t];
-            sh.list[warp][t] = make_float4(cx.pts[(size_t)j * 3], cx.pts[(size_t)j * 3 + 1], cx.pts[(size_t)j * 3 + 2], 0.f);
+            float qx, qy, qz;
+            cx.point(sh.listIdx[warp][t], qx, qy, qz);
+            sh.list[warp][t] = make_float4(qx, qy, qz, 0.f);
         }
     }
     __syncwarp();
@@ -116,11 +128,7 @@ __device__ __forceinline__ void process_cell(const CloudCtx& cx, SelShared& sh, 
         const int i = c0 + pi;
         const bool valid = pi < cnt;
         float px = 0.f, py = 0.f, pz = 0.f;
-        if (valid) {
-            px = cx.pts[(size_t)i * 3];
-            py = cx.pts[(size_t)i * 3 + 1];
-            pz = cx.pts[(size_t)i * 3 + 2];
-        }
+        if (valid) cx.point(i, px, py, pz);
         int blocked = 0;  // an accepted point of an earlier phase / earlier chunk lies within r
         if (listOk) {
             for (int t = slice; t < L; t += slices) {
@@ -135,9 +143,11 @@ __device__ __forceinline__ void process_cell(const CloudCtx& cx, SelShared& sh, 
                     hi2 = c0;
                 }
                 for (int j = lo2 + slice; j < hi2; j += slices)
-                    if (cx.flag(j))
-                        blocked |= dist2_ref(px, py, pz, cx.pts[(size_t)j * 3], cx.pts[(size_t)j * 3 + 1],
-                                             cx.pts[(size_t)j * 3 + 2]) <= cx.thr;
+                    if (cx.flag(j)) {
+                        float qx, qy, qz;
+                        cx.point(j, qx, qy, qz);
+                        blocked |= dist2_ref(px, py, pz, qx, qy, qz) <= cx.thr;
+                    }
             }
         }
         for (int off = pointLanes; off < 32; off <<= 1) blocked |= __shfl_xor_sync(MC_FULL_MASK, blocked, off);
@@ -178,6 +188,8 @@ __global__ void __launch_bounds__(kSelThreads)
     SelShared& sh = *reinterpret_cast<SelShared*>(smemRaw);
     unsigned char* sFlags = smemRaw + sizeof(SelShared);
     unsigned short* cellList = reinterpret_cast<unsigned short*>(sFlags + kSelFlagBytes);
+    int2* sCells = reinterpret_cast<int2*>(sFlags + kSelFlagBytes + kCellListCap * sizeof(unsigned short));
+    float* sPts = reinterpret_cast<float*>(sCells + kStageCells);
     const int lane = lane_id(), warp = threadIdx.x >> 5;
     const unsigned ltMask = (1u << lane) - 1u;
 
@@ -198,12 +210,14 @@ __global__ void __launch_bounds__(kSelThreads)
     const int cellsPerCloud = n * n * n;
     const int2* cells = cellIdx + (size_t)b * cellsPerCloud;
     const bool useLists = cellsPerCloud <= kCellListCap;
+    const bool stageCells = cellsPerCloud <= kStageCells;
 
     // extent of this cloud inside the sorted array (the sort is batch-major) + non-empty cells per phase
     {
         int lo = INT_MAX, hi = 0;
         for (int c = threadIdx.x; c < cellsPerCloud; c += kSelThreads) {
             int2 ce = cells[c];
+            if (stageCells) sCells[c] = ce;
             if (ce.y > ce.x) {
                 lo = min(lo, ce.x);
                 hi = max(hi, ce.y);
@@ -227,6 +241,11 @@ __global__ void __launch_bounds__(kSelThreads)
     const bool inSmem = nCloud <= kSelFlagBytes;
     if (inSmem)
         for (int t = threadIdx.x; t < nCloud; t += kSelThreads) sFlags[t] = 0;
+    // every later access to the cloud's points and cell rows is then a shared-memory access: the per-cell work is a
+    // chain of dependent loads, and first-touch global misses were what made it slow
+    const bool stagePts = nCloud <= kStagePts;
+    if (stagePts)
+        for (int t = threadIdx.x; t < nCloud * 3; t += kSelThreads) sPts[t] = pts[(size_t)cLo * 3 + t];
     if (useLists) {
         if (threadIdx.x == 0) {
             int run = 0;
@@ -237,7 +256,7 @@ __global__ void __launch_bounds__(kSelThreads)
         }
         __syncthreads();
         for (int c = threadIdx.x; c < cellsPerCloud; c += kSelThreads) {
-            int2 ce = cells[c];
+            int2 ce = stageCells ? sCells[c] : cells[c];
             if (ce.y > ce.x) {
                 const int x = c / (n * n), y = (c / n) % n, z = c % n;
                 const int p = kPhaseOfOffset[(x % 3) * 9 + (y % 3) * 3 + (z % 3)];
@@ -249,7 +268,9 @@ __global__ void __launch_bounds__(kSelThreads)
 
     CloudCtx cx;
     cx.cells = cells;
+    cx.sCells = stageCells ? sCells : nullptr;
     cx.pts = pts;
+    cx.sPts = stagePts ? sPts : nullptr;
     cx.sFlags = inSmem ? sFlags : nullptr;
     cx.gFlags = selGlobal;
     cx.cLo = cLo;
@@ -266,7 +287,7 @@ __global__ void __launch_bounds__(kSelThreads)
                 for (int t = beg + warp; t < end; t += kSelWarps) {
                     const int c = cellList[t];
                     const int x = c / (n * n), y = (c / n) % n, z = c % n;
-                    process_cell(cx, sh, warp, lane, x, y, z, cells[c], ph);
+                    process_cell(cx, sh, warp, lane, x, y, z, cx.cell(c), ph);
                 }
                 if (end == beg) continue;  // nothing was written in this phase: no barrier needed (uniform)
             } else {
@@ -278,7 +299,7 @@ __global__ void __launch_bounds__(kSelThreads)
                     const int tx = c / (tY * tZ), rem = c - tx * (tY * tZ);
                     const int ty = rem / tZ, tz = rem - ty * tZ;
                     const int x = tx * 3 + 1 + ox, y = ty * 3 + 1 + oy, z = tz * 3 + 1 + oz;
-                    const int2 own = cells[(x * n + y) * n + z];
+                    const int2 own = cx.cell((x * n + y) * n + z);
                     if (own.y <= own.x) continue;
                     process_cell(cx, sh, warp, lane, x, y, z, own, ph);
                 }
@@ -351,7 +372,8 @@ __global__ void __launch_bounds__(kSelThreads)
     }
 }
 
-constexpr size_t kSelSmemBytes = sizeof(SelShared) + kSelFlagBytes + kCellListCap * sizeof(unsigned short);
+constexpr size_t kSelSmemBytes = sizeof(SelShared) + kSelFlagBytes + kCellListCap * sizeof(unsigned short) +
+                                 kStageCells * sizeof(int2) + kStagePts * 3 * sizeof(float);
 
 }  // namespace
 }  // namespace mc
