@@ -38,7 +38,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32)
     // lanes 0..26: (lo,hi) of neighbour cell `lane`
     int lo = 0, hi = 0;
     if (lane < 27) {
-        int x = cx + kOffsNeigh[lane][0], y = cy + kOffsNeigh[lane][1], z = cz + kOffsNeigh[lane][2];
+        // kOffsNeigh[lane] in closed form (x cycles +1,0,-1 fastest, find_neighbors.cu:282-291): a lane-indexed
+        // constant-memory load would serialise over the 27 distinct addresses
+        int x = cx + 1 - lane % 3, y = cy + 1 - (lane / 3) % 3, z = cz + 1 - lane / 9;
         if (x >= 0 && x < n && y >= 0 && y < n && z >= 0 && z < n) {
             int2 c = cellIdx[(((size_t)b * n + x) * n + y) * n + z];
             lo = c.x;
@@ -112,7 +114,9 @@ __device__ __forceinline__ void sweep_sample(int i, bool scaleInv, int n, float 
     const float thr = exact_radius_threshold(f.radius);
     int lo = 0, hi = 0;
     if (lane < 27) {
-        int x = cx + kOffsNeigh[lane][0], y = cy + kOffsNeigh[lane][1], z = cz + kOffsNeigh[lane][2];
+        // kOffsNeigh[lane] in closed form (x cycles +1,0,-1 fastest, find_neighbors.cu:282-291): a lane-indexed
+        // constant-memory load would serialise over the 27 distinct addresses
+        int x = cx + 1 - lane % 3, y = cy + 1 - (lane / 3) % 3, z = cz + 1 - lane / 9;
         if (x >= 0 && x < n && y >= 0 && y < n && z >= 0 && z < n) {
             int2 c = cellIdx[(((size_t)b * n + x) * n + y) * n + z];
             lo = c.x;

@@ -71,6 +71,7 @@ struct CloudCtx {
     unsigned char* gFlags;        // global flags (index: sorted position) when the cloud does not fit
     int cLo;
     int n;
+    int offX, offY, offZ;         // kOffsPool[lane]: read ONCE per thread (a lane-indexed constant load serialises)
     float thr;                    // exact squared-distance threshold of the cloud's radius
     __device__ __forceinline__ unsigned char flag(int j) const {
         return sFlags ? sFlags[j - cLo] : __ldcg(&gFlags[j]);
@@ -91,7 +92,7 @@ __device__ __forceinline__ void process_cell(const CloudCtx& cx, SelShared& sh, 
     // ---- A: compact the accepted points of the 26 neighbour cells into the warp's list
     int nlo = 0, nhi = 0;
     if (lane < 27 && lane != kSelfOffset) {
-        int qx = x + kOffsPool[lane][0], qy = y + kOffsPool[lane][1], qz = z + kOffsPool[lane][2];
+        int qx = x + cx.offX, qy = y + cx.offY, qz = z + cx.offZ;
         if (qx >= 0 && qx < n && qy >= 0 && qy < n && qz >= 0 && qz < n) {
             int2 ce = cx.cell((qx * n + qy) * n + qz);
             nlo = ce.x;
@@ -275,6 +276,9 @@ __global__ void __launch_bounds__(kSelThreads)
     cx.gFlags = selGlobal;
     cx.cLo = cLo;
     cx.n = n;
+    cx.offX = lane < 27 ? kOffsPool[lane][0] : 0;
+    cx.offY = lane < 27 ? kOffsPool[lane][1] : 0;
+    cx.offZ = lane < 27 ? kOffsPool[lane][2] : 0;
     {
         const float ext = max_extent(mn, mx, b);
         cx.thr = exact_radius_threshold(scaleInv ? __fmul_rn(radius, ext) : radius);
