@@ -131,7 +131,7 @@ long long mc_spatial_conv_workspace_floats(int numSamples, int numInFeatures, in
  * indexes (tf_ops/spatial_conv.cu:49-73,172). */
 int mc_spatial_conv(int avg, int scaleInv, int numNeighbors, const int* dNumNeighbors, int numInFeatures,
                     int numOutFeatures, int numSamples, const int* dNumSamples, int combin, float radius,
-                    const float* pts, const int* batchIds, const float* features, const float* pdfs,
+                    int batchSize, const float* pts, const int* batchIds, const float* features, const float* pdfs,
                     const float* samples, const int* startIdx, const int* pairs, const float* aabbMin,
                     const float* aabbMax, const float* W1, const float* b1, const float* W2, const float* b2,
                     const float* Wout, const float* bout, float* workspace, float* outFeatures, void* stream);

@@ -49,7 +49,7 @@ SIGNATURES = {
                                      _ptr, _c_int, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr]),
     "mc_get_sampled_features": (_c_int, [_c_int, _ptr, _c_int, _ptr, _ptr, _ptr, _ptr]),
     "mc_spatial_conv_workspace_floats": (_c_ll, [_c_int, _c_int, _c_int, _c_int]),
-    "mc_spatial_conv": (_c_int, [_c_int, _c_int, _c_int, _ptr, _c_int, _c_int, _c_int, _ptr, _c_int, _c_float] +
+    "mc_spatial_conv": (_c_int, [_c_int, _c_int, _c_int, _ptr, _c_int, _c_int, _c_int, _ptr, _c_int, _c_float, _c_int] +
                         [_ptr] * 18),
     "mc_scale_shift_act": (_c_int, [_c_int, _ptr, _c_int, _ptr, _ptr, _ptr, _c_int, _ptr, _ptr]),
     "mc_dense_layer": (_c_int, [_c_int, _ptr, _c_int, _c_int, _c_int, _ptr, _ptr, _ptr, _c_int, _ptr, _ptr, _ptr, _ptr,

@@ -238,7 +238,7 @@ def spatial_conv(pts, feats, bids, pdfs, samples, start, pairs, aabb_min, aabb_m
     ws_n = lib.mc_spatial_conv_workspace_floats(M, C, num_out_features, int(combin))
     ws = torch.empty((ws_n,), dtype=_f32, device=dev) if ws_n > 0 else None
     check(lib.mc_spatial_conv(int(avg), int(scale_inv), K, _p(k_dev), C, num_out_features, M, _p(m_dev), int(combin),
-                              float(radius), _p(pts), _p(bids), _p(feats), _p(pdfs), _p(samples), _p(start),
+                              float(radius), aabb_min.shape[0], _p(pts), _p(bids), _p(feats), _p(pdfs), _p(samples), _p(start),
                               _p(pairs), _p(aabb_min), _p(aabb_max), _p(w1), _p(b1), _p(w2), _p(b2), _p(wout),
                               _p(bout), _p(ws), _p(out), _stream()))
     return out

@@ -48,7 +48,7 @@ def test_constants_and_status_plumbing():
     assert st == 1 and b"radius" in lib.mc_last_error()
     with pytest.raises(ValueError):
         check(st)
-    st = lib.mc_spatial_conv(1, 1, 0, None, 12, 12, 0, None, 0, ctypes.c_float(0.1), *([None] * 18))
+    st = lib.mc_spatial_conv(1, 1, 0, None, 12, 12, 0, None, 0, ctypes.c_float(0.1), 1, *([None] * 18))
     assert st == 1 and b"multiple of the block size" in lib.mc_last_error()
 
 
