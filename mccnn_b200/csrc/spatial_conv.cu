@@ -11,9 +11,10 @@
 //     sample has, and each 128-bit shared-memory broadcast of parameters feeds two pairs;
 //   * the whole block MLP of a pair lives in registers (first layer packed as (w_x, w_y, w_z, b) per neuron);
 //   * the Monte-Carlo sum is a SEGMENTED reduction over the lanes of a tile: for each sample present in the tile the
-//     lanes' contributions are masked and closed with a 9-shuffle reduce-scatter per block; partial sums of a sample
-//     that continues into the next tile are carried in a register.  One store per (sample, neuron), NO atomics, and
-//     a summation order that is a pure function of the neighbour list: bit-reproducible, unlike the reference.
+//     lanes' contributions are masked and closed with a 31-shuffle reduce-scatter over the chunk's 32 neurons, after
+//     which lane l holds neuron l (one coalesced 128-byte store); partial sums of a sample that continues into the
+//     next tile are carried in a register.  NO atomics, and a summation order that is a pure function of the
+//     neighbour list: bit-reproducible, unlike the reference.
 // FP32 FFMA throughout: parity with the reference is 1e-5 relative, which TF32 tensor-core inputs (10-bit
 // mantissa) cannot meet, and at 8x8 per block the layers are not GEMM-shaped ("why no tensor cores").
 #include "common.cuh"
@@ -105,36 +106,17 @@ __device__ __forceinline__ void block_mlp2(const float4* __restrict__ w, const P
     }
 }
 
-// sum of 8 per-lane values over the 32 lanes: afterwards EVERY lane holds the total of value index
-// ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)    (9 shuffles)
-__device__ __forceinline__ float reduce8_over_warp(float (&v)[8], int lane) {
-    {
-        const bool up = (lane & 16) != 0;
+// one butterfly level of the reduce-scatter over the 32 lanes: lanes with bit OFF set keep the upper half of the
+// live values.  After levels 16, 8, 4, 2, 1 lane l holds the warp total of value index l.
+template <int OFF>
+__device__ __forceinline__ void reduce_scatter_step(float (&v)[kChunkNeurons], int lane) {
+    const bool upper = (lane & OFF) != 0;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float send = up ? v[k] : v[k + 4];
-            const float keep = up ? v[k + 4] : v[k];
-            v[k] = keep + __shfl_xor_sync(MC_FULL_MASK, send, 16);
-        }
+    for (int k = 0; k < OFF; ++k) {
+        const float send = upper ? v[k] : v[k + OFF];
+        const float keep = upper ? v[k + OFF] : v[k];
+        v[k] = keep + __shfl_xor_sync(MC_FULL_MASK, send, OFF);
     }
-    {
-        const bool up = (lane & 8) != 0;
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const float send = up ? v[k] : v[k + 2];
-            const float keep = up ? v[k + 2] : v[k];
-            v[k] = keep + __shfl_xor_sync(MC_FULL_MASK, send, 8);
-        }
-    }
-    {
-        const bool up = (lane & 4) != 0;
-        const float send = up ? v[0] : v[1];
-        const float keep = up ? v[1] : v[0];
-        v[0] = keep + __shfl_xor_sync(MC_FULL_MASK, send, 4);
-    }
-    v[0] += __shfl_xor_sync(MC_FULL_MASK, v[0], 2);
-    v[0] += __shfl_xor_sync(MC_FULL_MASK, v[0], 1);
-    return v[0];
 }
 
 template <int MODE>
@@ -196,10 +178,8 @@ __global__ void __launch_bounds__(kConvWarps * 32) spatial_conv_kernel(const Con
     const int P0 = min(a.start[s0], K);
     const int P1 = min((s1 < M) ? a.start[s1] : K, K);
 
-    // neuron (inside a block) whose total this lane holds after reduce8_over_warp
-    const int tOwn = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-    float carry[kChunkBlocks] = {0.f, 0.f, 0.f, 0.f};
-    int openSample = -1;  // sample whose partial sums sit in carry[]
+    float carry = 0.0f;   // partial sum (neuron n) of the sample that continues from the previous tile
+    int openSample = -1;  // that sample
 
     for (int tile = P0; tile < P1; tile += kTile) {
         PairState ps[2];
@@ -246,22 +226,27 @@ __global__ void __launch_bounds__(kConvWarps * 32) spatial_conv_kernel(const Con
                 if (ps[u].i >= 0) fs[u] = a.feats[ps[u].j] * ps[u].invw;
         }
 
+        float va[kChunkNeurons], vb[kChunkNeurons];  // f * kappa / (pdf * cnt) of this lane's two pairs
 #pragma unroll
         for (int q = 0; q < kChunkBlocks; ++q) {
             const int blk = chunk * kChunkBlocks + q;
-            if (blk >= a.numBlocks) continue;  // warp-uniform
+            if (blk >= a.numBlocks) {  // warp-uniform
+#pragma unroll
+                for (int t = 0; t < 8; ++t) va[q * 8 + t] = vb[q * 8 + t] = 0.0f;
+                continue;
+            }
             // parameters are re-read from shared memory (128-bit broadcasts) for every tile; the empty asm keeps the
             // compiler from hoisting the loop-invariant loads into registers (it spills otherwise)
             int wOff = q * kBlockParams;
             asm volatile("" : "+r"(wOff));
-            float va[8], vb[8];
-            block_mlp2(reinterpret_cast<const float4*>(sW + wOff), ps[0], ps[1], va, vb);
+            float ka[8], kb[8];
+            block_mlp2(reinterpret_cast<const float4*>(sW + wOff), ps[0], ps[1], ka, kb);
             // weight each kernel value by the pair's feature / (pdf * cnt)
             if (MODE == kSingleIn) {
 #pragma unroll
                 for (int t = 0; t < 8; ++t) {
-                    va[t] *= fs[0];
-                    vb[t] *= fs[1];
+                    va[q * 8 + t] = ka[t] * fs[0];
+                    vb[q * 8 + t] = kb[t] * fs[1];
                 }
             } else {
 #pragma unroll
@@ -282,27 +267,32 @@ __global__ void __launch_bounds__(kConvWarps * 32) spatial_conv_kernel(const Con
 #pragma unroll
                     for (int t = 0; t < 8; ++t) {
                         if (u == 0)
-                            va[t] *= f[t] * ps[0].invw;
+                            va[q * 8 + t] = ka[t] * (f[t] * ps[0].invw);
                         else
-                            vb[t] *= f[t] * ps[1].invw;
+                            vb[q * 8 + t] = kb[t] * (f[t] * ps[1].invw);
                     }
                 }
             }
-            // segmented sum over the samples of the tile
-            for (int cur = iFirst; cur <= iLast; ++cur) {
-                const bool m0 = ps[0].i == cur, m1 = ps[1].i == cur;
-                if (__ballot_sync(MC_FULL_MASK, m0 || m1) == 0u) continue;  // sample without pairs
-                float w8[8];
+        }
+        // segmented sum over the samples of the tile: mask, then one 31-shuffle reduce-scatter over the 32 neurons of
+        // the chunk (independent shuffles per butterfly level), after which lane l holds neuron chunk*32 + l
+        for (int cur = iFirst; cur <= iLast; ++cur) {
+            const bool m0 = ps[0].i == cur, m1 = ps[1].i == cur;
+            if (__ballot_sync(MC_FULL_MASK, m0 || m1) == 0u) continue;  // sample without pairs
+            float w[kChunkNeurons];
 #pragma unroll
-                for (int t = 0; t < 8; ++t) w8[t] = (m0 ? va[t] : 0.0f) + (m1 ? vb[t] : 0.0f);
-                float tot = reduce8_over_warp(w8, lane);
-                if (cur == openSample) tot += carry[q];
-                if (cur < iLast || lastComplete) {
-                    const int nn = blk * 8 + tOwn;
-                    if ((lane & 3) == 0 && nn < a.nOut) a.out[(size_t)cur * a.outStride + nn] = tot;
-                } else {
-                    carry[q] = tot;  // the sample continues in the next tile
-                }
+            for (int t = 0; t < kChunkNeurons; ++t) w[t] = (m0 ? va[t] : 0.0f) + (m1 ? vb[t] : 0.0f);
+            reduce_scatter_step<16>(w, lane);
+            reduce_scatter_step<8>(w, lane);
+            reduce_scatter_step<4>(w, lane);
+            reduce_scatter_step<2>(w, lane);
+            reduce_scatter_step<1>(w, lane);
+            float tot = w[0];
+            if (cur == openSample) tot += carry;
+            if (cur < iLast || lastComplete) {
+                if (n < a.nOut) a.out[(size_t)cur * a.outStride + n] = tot;  // one coalesced 128-byte store per warp
+            } else {
+                carry = tot;  // the sample continues in the next tile
             }
         }
         openSample = lastComplete ? -1 : iLast;
@@ -357,10 +347,12 @@ extern "C" int mc_spatial_conv(int avg, int scaleInv, int numNeighbors, const in
     const int nOut = combin ? C * numOutFeatures : C;
     const int nb = (nOut + 7) / 8;
     const int chunks = cdiv(nb, kChunkBlocks);
-    // run length per warp: aim at ~6 tiles of pairs per warp so that the partially filled last tile is cheap
+    // run length per warp: ~3 tiles of pairs per warp (the partially filled last tile stays cheap) -- but the op is
+    // latency bound, so never at the price of leaving the GPU short of warps
     long long avgK = numNeighbors / (long long)numSamples;
-    int G = (int)(384 / (avgK > 0 ? avgK : 1));
+    int G = (int)(192 / (avgK > 0 ? avgK : 1));
     G = G < 1 ? 1 : (G > 16 ? 16 : G);
+    while (G > 1 && (long long)cdiv(numSamples, G) * chunks < 2048) --G;
     ConvArgs a;
     a.avg = avg != 0;
     a.scaleInv = scaleInv != 0;
