@@ -145,6 +145,118 @@ class HostForward:
         return h2d, d2h
 
 
+class PipelinedForward:
+    """Throughput mode: `depth` independent forwards in flight on one GPU.
+
+    One MCClassS-sized forward is latency bound and occupies a fraction of the 148 SMs at any moment (a chain of small
+    kernels); a server that has several batches queued can overlap them.  This class keeps `depth` PlannedForward
+    engines -- each with its own CUDA graph and static buffers, all sharing the recorded plan sizes and the weights --
+    and replays them round-robin on `depth` streams.  Every forward does the full work of the sequential one and
+    produces bit-identical results; only the scheduling changes.
+
+    submit(pts, bids, feats) enqueues one forward on the next lane and returns its ticket; result(ticket) waits for
+    that forward only and returns (out, overflow_flag) device tensors (valid until the lane is reused)."""
+
+    def __init__(self, fn, out_rows, depth=4, slack=1.3, multistream=True):
+        self.depth = depth
+        self.engines = [PlannedForward(fn, out_rows, use_graph=True, slack=slack, multistream=multistream)
+                        for _ in range(depth)]
+        self.streams = None
+        self._events = [None] * depth
+        self._results = [None] * depth
+        self._next = 0
+
+    def calibrate(self, batches):
+        plan = self.engines[0].calibrate(batches)
+        for e in self.engines[1:]:  # same sizes, own Plan object (own overflow flag, own graph)
+            p = _rt.Plan(slack=plan.slack, granule=plan.granule)
+            p.sizes, p.flags = list(plan.sizes), list(plan.flags)
+            p.finalize()
+            e.plan, e._shape_key, e.graph = p, self.engines[0]._shape_key, None
+        dev = batches[0][0].device
+        self.streams = [torch.cuda.Stream(device=dev) for _ in range(self.depth)]
+        for e, s in zip(self.engines, self.streams):  # capture every lane's graph up front
+            with torch.cuda.stream(s):
+                e.run_async(*batches[0])
+        torch.cuda.synchronize(dev)
+        return plan
+
+    def submit(self, pts, bids, feats):
+        lane = self._next
+        self._next = (self._next + 1) % self.depth
+        s = self.streams[lane]
+        s.wait_stream(torch.cuda.current_stream())  # inputs produced on the caller's stream
+        with torch.cuda.stream(s):
+            out, flag = self.engines[lane].run_async(pts, bids, feats)
+            ev = torch.cuda.Event()
+            ev.record(s)
+        self._events[lane], self._results[lane] = ev, (out, flag)
+        return lane
+
+    def result(self, ticket, wait_on_host=False):
+        ev = self._events[ticket]
+        if wait_on_host:
+            ev.synchronize()
+        else:
+            torch.cuda.current_stream().wait_event(ev)
+        return self._results[ticket]
+
+    def join(self):
+        for ev in self._events:
+            if ev is not None:
+                torch.cuda.current_stream().wait_event(ev)
+
+
+class PipelinedHostForward:
+    """End-to-end throughput mode for host-resident batches: each lane of a PipelinedForward owns pinned staging, so
+    the H2D copy of batch i+1, the forward of batch i and the D2H of batch i-1 overlap.  submit() takes CPU tensors
+    (ideally pinned) and returns a ticket; result(ticket) blocks until that batch's logits are on the host."""
+
+    def __init__(self, pipe, device):
+        self.pipe = pipe
+        self.device = torch.device(device)
+        d = pipe.depth
+        self._dev_in = [None] * d
+        self._out_host = [None] * d
+        self._flag_host = [torch.zeros((1,), dtype=torch.int32).pin_memory() for _ in range(d)]
+        self._events = [None] * d
+        self._inputs = [None] * d
+
+    def submit(self, pts_host, bids_host, feats_host):
+        lane = self.pipe._next
+        if self._events[lane] is not None:
+            self._events[lane].synchronize()  # the lane's previous result has reached the host
+        s = self.pipe.streams[lane]
+        if self._dev_in[lane] is None or tuple(self._dev_in[lane][0].shape) != tuple(pts_host.shape):
+            self._dev_in[lane] = tuple(torch.empty(t.shape, dtype=t.dtype, device=self.device)
+                                       for t in (pts_host, bids_host, feats_host))
+        with torch.cuda.stream(s):
+            for dst, src in zip(self._dev_in[lane], (pts_host, bids_host, feats_host)):
+                dst.copy_(src, non_blocking=True)
+        ticket = self.pipe.submit(*self._dev_in[lane])
+        out, flag = self.pipe._results[ticket]
+        if self._out_host[lane] is None or tuple(self._out_host[lane].shape) != tuple(out.shape):
+            self._out_host[lane] = torch.empty(out.shape, dtype=out.dtype).pin_memory()
+        with torch.cuda.stream(s):
+            self._out_host[lane].copy_(out, non_blocking=True)
+            self._flag_host[lane].copy_(flag, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(s)
+        self._events[lane] = ev
+        self._inputs[lane] = (pts_host, bids_host, feats_host)
+        return ticket
+
+    def result(self, ticket):
+        self._events[ticket].synchronize()
+        if int(self._flag_host[ticket][0]) != 0:  # planned capacity exceeded: exact re-run of this batch
+            eng = self.pipe.engines[ticket]
+            eng.stats["overflows"] += 1
+            with torch.cuda.stream(self.pipe.streams[ticket]):
+                self._out_host[ticket].copy_(eng._record(*self._dev_in[ticket]))
+            self.pipe.streams[ticket].synchronize()
+        return self._out_host[ticket]
+
+
 # ---- data-parallel sharding (one process per GPU) ---------------------------------------------------------------
 
 def shard_range(batch_size, rank, world_size):
