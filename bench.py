@@ -151,7 +151,7 @@ def run_ours(args, rank, world, dev):
     from mccnn_b200 import ops, variables
     from mccnn_b200._lib import lib
     from mccnn_b200.engine import (PlannedForward, PipelinedForward, HostForward, PipelinedHostForward,
-                                   gather_logits)
+                                   gather_logits, pack_batch)
     from mccnn_b200.models import MCClassS
 
     B, P, k = args.batch, args.points, args.k
@@ -216,15 +216,17 @@ def run_ours(args, rank, world, dev):
     # an overlapped region); one event pair around exactly K steps.
     depth = max(1, args.pipeline)
     n_pipe = max(n_batches, int(math.ceil(140e6 / (B * P * 20.0))))     # 20 B of input per point -> > 126 MB L2
-    pipe_res = list(resident)
+    # resident batches in the single-block layout the captured graphs read (points | batch ids | features)
+    pipe_res = [pack_batch(*r) for r in resident]
     for i in range(n_batches, n_pipe):
-        pipe_res.append(tuple(torch.from_numpy(a).to(dev) for a in make_batch(B, P, "sphere", seed=1000 * rank + i)))
+        pipe_res.append(pack_batch(*(torch.from_numpy(a).to(dev)
+                                     for a in make_batch(B, P, "sphere", seed=1000 * rank + i))))
     pipe = PipelinedForward(fn, B, depth=depth, slack=1.3)
     pipe.calibrate(resident)
     pflags = torch.zeros((1,), dtype=torch.int32, device=dev)
 
     def pstep(i):
-        ticket = pipe.submit(*pipe_res[i % n_pipe])
+        ticket = pipe.submit_packed(pipe_res[i % n_pipe])
         if world > 1:
             out, flag = pipe.result(ticket)
             gather_logits(out, B * world, world)
@@ -325,18 +327,19 @@ def run_ours(args, rank, world, dev):
     # ---- e2e: host buffers, H2D + forward + D2H inside the timed call
     # (a) one call at a time (latency), (b) `depth` calls in flight (throughput) -- every step copies its inputs from
     # pinned host memory and its logits + overflow flag back, and every result is read on the host
+    pinned_blocks = [pack_batch(*h, pin=True) for h in pinned]   # the data loader's pinned staging buffers
     hf = HostForward(eng, dev)
     for i in range(3):
-        hf(*pinned[i % n_batches])
+        hf.call_packed(pinned_blocks[i % n_batches])
     torch.cuda.synchronize(dev)
     t0 = time.perf_counter()
     for i in range(args.steps):
-        res = hf(*pinned[i % n_batches])
+        res = hf.call_packed(pinned_blocks[i % n_batches])
     e2e_latency_s = (time.perf_counter() - t0) / args.steps
     phf = PipelinedHostForward(pipe, dev)
     checksum = 0.0
     for i in range(2 * depth):
-        phf.submit(*pinned[i % n_batches])
+        phf.submit_packed(pinned_blocks[i % n_batches])
     for lane in range(depth):
         phf.result(lane)
     if world > 1:
@@ -345,7 +348,7 @@ def run_ours(args, rank, world, dev):
     t0 = time.perf_counter()
     tickets = []
     for i in range(args.steps):
-        tk = phf.submit(*pinned[i % n_batches])   # blocks until this lane's previous result is on the host
+        tk = phf.submit_packed(pinned_blocks[i % n_batches])   # blocks until this lane's previous result is on the host
         tickets.append(tk)
         if len(tickets) > depth:                   # consume the oldest result on the host
             res = phf.result(tickets.pop(0))

@@ -1,4 +1,4 @@
-"""Recorded, sync-free, CUDA-graph-captured forward passes and their data-parallel sharding.
+"""Recorded, sync-free, CUDA-graph-captured forward passes, their pipelining and their data-parallel sharding.
 
 `PlannedForward` wraps any network function written against the reference API
 (fn(points, batchIds, features) -> tensor, e.g. models.MCClassS.create_network):
@@ -10,12 +10,48 @@
 If an input ever needs more rows than planned, a device flag comes back with the result; the batch is then
 re-run exactly and the plan is re-recorded (results are never silently truncated).
 
+The graph reads its three inputs from ONE contiguous static block and leaves logits + overflow flag in ONE contiguous
+result block, so a host-resident batch costs exactly one H2D copy, one graph launch and one D2H copy
+(`HostForward`).  `PipelinedForward` / `PipelinedHostForward` keep several such forwards in flight on one GPU.
+
 `shard_batch` / `gather_logits` implement the multi-GPU partition of BASELINE.json's north_star: independent clouds
 of a packed batch are split contiguously over the ranks and ONE all_gather of the per-cloud logits closes the step.
 """
 import torch
 
 from . import runtime as _rt
+
+_ALIGN = 256
+
+
+def _layout(tensors):
+    """Byte offsets of (points, batchIds, features) inside one packed block, each 256-byte aligned."""
+    offs, total = [], 0
+    for t in tensors:
+        offs.append(total)
+        total += (t.numel() * t.element_size() + _ALIGN - 1) // _ALIGN * _ALIGN
+    return offs, max(total, _ALIGN)
+
+
+def _views(block, like):
+    offs, _ = _layout(like)
+    out = []
+    for o, t in zip(offs, like):
+        nbytes = t.numel() * t.element_size()
+        out.append(block[o:o + nbytes].view(t.dtype).view(t.shape))
+    return tuple(out)
+
+
+def pack_batch(pts, bids, feats, pin=False):
+    """Pack a batch into the single-block layout the captured graph reads (same device as the inputs; pinned host
+    memory if pin=True).  Returns a uint8 tensor."""
+    _, total = _layout((pts, bids, feats))
+    block = torch.empty((total,), dtype=torch.uint8, device=pts.device)
+    if pin:
+        block = block.pin_memory()
+    for v, t in zip(_views(block, (pts, bids, feats)), (pts, bids, feats)):
+        v.copy_(t)
+    return block
 
 
 class PlannedForward:
@@ -29,8 +65,11 @@ class PlannedForward:
         self.slack = slack
         self.plan = None
         self.graph = None
-        self._static_in = None
-        self._static_out = None
+        self._in_block = None     # static packed input block the graph reads
+        self._static_in = None    # typed views of it
+        self._result = None       # static float32 block: out_rows * F logits, then the overflow flag (int32 bits)
+        self._out_view = None
+        self._flag_view = None
         self._shape_key = None
         self.stats = {"records": 0, "captures": 0, "replays": 0, "overflows": 0}
 
@@ -49,7 +88,11 @@ class PlannedForward:
             return self.fn(pts, bids, feats)
 
     def _capture(self, pts, bids, feats):
-        self._static_in = (pts.clone(), bids.clone(), feats.clone())
+        _, total = _layout((pts, bids, feats))
+        self._in_block = torch.empty((total,), dtype=torch.uint8, device=pts.device)
+        self._static_in = _views(self._in_block, (pts, bids, feats))
+        for v, t in zip(self._static_in, (pts, bids, feats)):
+            v.copy_(t)
         self.plan.begin(pts.device)
         side = torch.cuda.Stream(device=pts.device)
         side.wait_stream(torch.cuda.current_stream())
@@ -58,33 +101,52 @@ class PlannedForward:
         torch.cuda.current_stream().wait_stream(side)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            self._static_out = self._planned(*self._static_in)
+            self.plan.overflow.zero_()
+            out = self._planned(*self._static_in)
+            rows, cols = self.out_rows, out.shape[1]
+            self._result = torch.empty((rows * cols + 1,), dtype=torch.float32, device=pts.device)
+            self._out_view = self._result[: rows * cols].view(rows, cols)
+            self._flag_view = self._result[rows * cols:].view(torch.int32)
+            self._out_view.copy_(out[:rows])
+            self._flag_view.copy_(self.plan.overflow)
         self.graph = g
         self.stats["captures"] += 1
+
+    def _ready(self, pts, bids, feats):
+        """True when a plan for these shapes exists (graph captured if use_graph)."""
+        key = (tuple(pts.shape), tuple(feats.shape))
+        if self.plan is None or key != self._shape_key:
+            return False
+        if self.plan.overflow is None:
+            self.plan.begin(pts.device)
+        if self.use_graph and self.graph is None:
+            self._capture(pts, bids, feats)
+        return True
 
     # -- public ------------------------------------------------------------------------------------------------
     def run_async(self, pts, bids, feats):
         """Enqueue one forward; returns (out[out_rows, F], overflow_flag int32[1]) device tensors, no host sync.
         The first call (and any call with new input shapes) records and therefore does synchronise."""
-        key = (tuple(pts.shape), tuple(feats.shape))
-        if self.plan is None or key != self._shape_key:
+        if not self._ready(pts, bids, feats):
             out = self._record(pts, bids, feats)
             return out, torch.zeros((1,), dtype=torch.int32, device=pts.device)
-        if self.plan.overflow is None:
-            self.plan.begin(pts.device)
-        self.plan.overflow.zero_()
         if not self.use_graph:
+            self.plan.overflow.zero_()
             out = self._planned(pts, bids, feats)
             return out[: self.out_rows], self.plan.overflow
-        if self.graph is None:
-            self._capture(pts, bids, feats)
-        sp, sb, sf = self._static_in
-        sp.copy_(pts, non_blocking=True)
-        sb.copy_(bids, non_blocking=True)
-        sf.copy_(feats, non_blocking=True)
+        for v, t in zip(self._static_in, (pts, bids, feats)):
+            v.copy_(t, non_blocking=True)
         self.graph.replay()
         self.stats["replays"] += 1
-        return self._static_out[: self.out_rows], self.plan.overflow
+        return self._out_view, self._flag_view
+
+    def run_packed(self, block):
+        """Like run_async for a batch already packed with pack_batch (device or pinned host memory): one copy into
+        the graph's input block, one graph launch.  Requires a captured graph (call run_async once before)."""
+        self._in_block.copy_(block, non_blocking=True)
+        self.graph.replay()
+        self.stats["replays"] += 1
+        return self._out_view, self._flag_view
 
     def __call__(self, pts, bids, feats):
         """Forward with the overflow check (one D2H of the flag); exact re-run + re-plan when a capacity was hit."""
@@ -109,35 +171,47 @@ class PlannedForward:
 
 
 class HostForward:
-    """End-to-end call for host-resident batches: pinned host buffers -> H2D -> planned forward -> D2H of the result
-    (and of the overflow flag) -> host tensor.  This is the user-facing equivalent of the reference's
+    """End-to-end call for host-resident batches: pinned host block -> ONE H2D copy -> graph launch -> ONE D2H copy of
+    logits + overflow flag -> host tensor.  This is the user-facing equivalent of the reference's
     `sess.run(logits, feed_dict)` (ModelNet/ModelNetEval.py:123-125)."""
 
     def __init__(self, engine, device):
         self.engine = engine
         self.device = torch.device(device)
-        self._dev = None
-        self._out_host = None
-        self._flag_host = torch.zeros((1,), dtype=torch.int32).pin_memory()
+        self._stage = None       # pinned packed staging for the three-tensor entry point
+        self._result_host = None
+
+    def _finish(self, unpack_for_rerun):
+        eng = self.engine
+        if self._result_host is None or self._result_host.numel() != eng._result.numel():
+            self._result_host = torch.empty(eng._result.shape, dtype=torch.float32).pin_memory()
+        self._result_host.copy_(eng._result, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        rows, cols = eng._out_view.shape
+        out = self._result_host[: rows * cols].view(rows, cols)
+        if int(self._result_host[rows * cols:].view(torch.int32)[0]) != 0:  # capacity exceeded: exact re-run, re-plan
+            eng.stats["overflows"] += 1
+            out = eng._record(*unpack_for_rerun()).cpu()
+        return out
 
     def __call__(self, pts_host, bids_host, feats_host):
-        """Arguments: CPU tensors (ideally pinned).  Returns a pinned CPU tensor [out_rows, F] (reused across calls)."""
-        if self._dev is None or tuple(self._dev[0].shape) != tuple(pts_host.shape) or \
-                tuple(self._dev[2].shape) != tuple(feats_host.shape):
-            self._dev = tuple(torch.empty(t.shape, dtype=t.dtype, device=self.device)
-                              for t in (pts_host, bids_host, feats_host))
-        for d, h in zip(self._dev, (pts_host, bids_host, feats_host)):
-            d.copy_(h, non_blocking=True)
-        out, flag = self.engine.run_async(*self._dev)
-        if self._out_host is None or tuple(self._out_host.shape) != tuple(out.shape):
-            self._out_host = torch.empty(out.shape, dtype=out.dtype).pin_memory()
-        self._out_host.copy_(out, non_blocking=True)
-        self._flag_host.copy_(flag, non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
-        if int(self._flag_host[0]) != 0:  # a planned capacity was exceeded: exact re-run, re-plan
-            self.engine.stats["overflows"] += 1
-            self._out_host.copy_(self.engine._record(*self._dev))
-        return self._out_host
+        """CPU tensors in (ideally pinned), pinned CPU logits [out_rows, F] out (buffer reused across calls)."""
+        eng = self.engine
+        key = (tuple(pts_host.shape), tuple(feats_host.shape))
+        if eng.graph is None or eng._shape_key != key:  # first calls: record, then capture (through device tensors)
+            return eng(*(t.to(self.device) for t in (pts_host, bids_host, feats_host))).cpu()
+        _, total = _layout((pts_host, bids_host, feats_host))
+        if self._stage is None or self._stage.numel() != total:
+            self._stage = torch.empty((total,), dtype=torch.uint8).pin_memory()
+        for v, t in zip(_views(self._stage, (pts_host, bids_host, feats_host)), (pts_host, bids_host, feats_host)):
+            v.copy_(t)
+        return self.call_packed(self._stage)
+
+    def call_packed(self, pinned_block):
+        """`pinned_block`: a batch packed with pack_batch(..., pin=True).  One H2D, one launch, one D2H."""
+        eng = self.engine
+        eng.run_packed(pinned_block)
+        return self._finish(lambda: tuple(v.clone() for v in eng._static_in))
 
     def bytes_per_call(self, pts_host, bids_host, feats_host, out_rows, out_cols):
         h2d = sum(t.numel() * t.element_size() for t in (pts_host, bids_host, feats_host))
@@ -154,8 +228,9 @@ class PipelinedForward:
     and replays them round-robin on `depth` streams.  Every forward does the full work of the sequential one and
     produces bit-identical results; only the scheduling changes.
 
-    submit(pts, bids, feats) enqueues one forward on the next lane and returns its ticket; result(ticket) waits for
-    that forward only and returns (out, overflow_flag) device tensors (valid until the lane is reused)."""
+    submit(pts, bids, feats) / submit_packed(block) enqueue one forward on the next lane and return its ticket;
+    result(ticket) makes the caller's stream (or the host) wait for that forward only and returns
+    (out, overflow_flag) device tensors, valid until the lane is reused."""
 
     def __init__(self, fn, out_rows, depth=4, slack=1.3, multistream=True):
         self.depth = depth
@@ -163,7 +238,6 @@ class PipelinedForward:
                         for _ in range(depth)]
         self.streams = None
         self._events = [None] * depth
-        self._results = [None] * depth
         self._next = 0
 
     def calibrate(self, batches):
@@ -176,22 +250,29 @@ class PipelinedForward:
         dev = batches[0][0].device
         self.streams = [torch.cuda.Stream(device=dev) for _ in range(self.depth)]
         for e, s in zip(self.engines, self.streams):  # capture every lane's graph up front
+            s.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(s):
                 e.run_async(*batches[0])
         torch.cuda.synchronize(dev)
         return plan
 
-    def submit(self, pts, bids, feats):
+    def _enqueue(self, run):
         lane = self._next
         self._next = (self._next + 1) % self.depth
         s = self.streams[lane]
         s.wait_stream(torch.cuda.current_stream())  # inputs produced on the caller's stream
         with torch.cuda.stream(s):
-            out, flag = self.engines[lane].run_async(pts, bids, feats)
+            run(self.engines[lane])
             ev = torch.cuda.Event()
             ev.record(s)
-        self._events[lane], self._results[lane] = ev, (out, flag)
+        self._events[lane] = ev
         return lane
+
+    def submit(self, pts, bids, feats):
+        return self._enqueue(lambda e: e.run_async(pts, bids, feats))
+
+    def submit_packed(self, block):
+        return self._enqueue(lambda e: e.run_packed(block))
 
     def result(self, ticket, wait_on_host=False):
         ev = self._events[ticket]
@@ -199,7 +280,8 @@ class PipelinedForward:
             ev.synchronize()
         else:
             torch.cuda.current_stream().wait_event(ev)
-        return self._results[ticket]
+        e = self.engines[ticket]
+        return e._out_view, e._flag_view
 
     def join(self):
         for ev in self._events:
@@ -208,53 +290,49 @@ class PipelinedForward:
 
 
 class PipelinedHostForward:
-    """End-to-end throughput mode for host-resident batches: each lane of a PipelinedForward owns pinned staging, so
-    the H2D copy of batch i+1, the forward of batch i and the D2H of batch i-1 overlap.  submit() takes CPU tensors
-    (ideally pinned) and returns a ticket; result(ticket) blocks until that batch's logits are on the host."""
+    """End-to-end throughput mode for host-resident batches: every lane of a PipelinedForward has its own pinned result
+    buffer, so the H2D copy of batch i+1, the forward of batch i and the D2H of batch i-1 overlap.
+    submit_packed(pinned_block) returns a ticket; result(ticket) blocks until that batch's logits are on the host."""
 
     def __init__(self, pipe, device):
         self.pipe = pipe
         self.device = torch.device(device)
-        d = pipe.depth
-        self._dev_in = [None] * d
-        self._out_host = [None] * d
-        self._flag_host = [torch.zeros((1,), dtype=torch.int32).pin_memory() for _ in range(d)]
-        self._events = [None] * d
-        self._inputs = [None] * d
+        self._result_host = [None] * pipe.depth
+        self._events = [None] * pipe.depth
+        self._blocks = [None] * pipe.depth
 
-    def submit(self, pts_host, bids_host, feats_host):
+    def submit_packed(self, pinned_block):
         lane = self.pipe._next
         if self._events[lane] is not None:
             self._events[lane].synchronize()  # the lane's previous result has reached the host
-        s = self.pipe.streams[lane]
-        if self._dev_in[lane] is None or tuple(self._dev_in[lane][0].shape) != tuple(pts_host.shape):
-            self._dev_in[lane] = tuple(torch.empty(t.shape, dtype=t.dtype, device=self.device)
-                                       for t in (pts_host, bids_host, feats_host))
+        eng, s = self.pipe.engines[lane], self.pipe.streams[lane]
+        if self._result_host[lane] is None:
+            self._result_host[lane] = torch.empty(eng._result.shape, dtype=torch.float32).pin_memory()
+        self.pipe._next = (lane + 1) % self.pipe.depth
         with torch.cuda.stream(s):
-            for dst, src in zip(self._dev_in[lane], (pts_host, bids_host, feats_host)):
-                dst.copy_(src, non_blocking=True)
-        ticket = self.pipe.submit(*self._dev_in[lane])
-        out, flag = self.pipe._results[ticket]
-        if self._out_host[lane] is None or tuple(self._out_host[lane].shape) != tuple(out.shape):
-            self._out_host[lane] = torch.empty(out.shape, dtype=out.dtype).pin_memory()
-        with torch.cuda.stream(s):
-            self._out_host[lane].copy_(out, non_blocking=True)
-            self._flag_host[lane].copy_(flag, non_blocking=True)
+            eng.run_packed(pinned_block)                                   # one H2D + one graph launch
+            self._result_host[lane].copy_(eng._result, non_blocking=True)  # one D2H: logits + overflow flag
             ev = torch.cuda.Event()
             ev.record(s)
-        self._events[lane] = ev
-        self._inputs[lane] = (pts_host, bids_host, feats_host)
-        return ticket
+        self._events[lane], self._blocks[lane] = ev, pinned_block
+        return lane
+
+    def submit(self, pts_host, bids_host, feats_host):
+        return self.submit_packed(pack_batch(pts_host, bids_host, feats_host, pin=True))
 
     def result(self, ticket):
         self._events[ticket].synchronize()
-        if int(self._flag_host[ticket][0]) != 0:  # planned capacity exceeded: exact re-run of this batch
-            eng = self.pipe.engines[ticket]
+        eng = self.pipe.engines[ticket]
+        rows, cols = eng._out_view.shape
+        host = self._result_host[ticket]
+        if int(host[rows * cols:].view(torch.int32)[0]) != 0:  # planned capacity exceeded: exact re-run of this batch
             eng.stats["overflows"] += 1
             with torch.cuda.stream(self.pipe.streams[ticket]):
-                self._out_host[ticket].copy_(eng._record(*self._dev_in[ticket]))
+                out = eng._record(*(v.clone() for v in eng._static_in))
+                eng.run_async(*(v.clone() for v in eng._static_in))  # re-capture for the following steps
             self.pipe.streams[ticket].synchronize()
-        return self._out_host[ticket]
+            return out.cpu()
+        return host[: rows * cols].view(rows, cols)
 
 
 # ---- data-parallel sharding (one process per GPU) ---------------------------------------------------------------

@@ -139,6 +139,52 @@ def test_capacity_overflow_is_detected_and_repaired():
     assert torch.equal(got, want)
 
 
+def test_pipelined_and_host_paths_match_exact():
+    """Several forwards in flight (PipelinedForward), packed single-copy inputs and the host-facing calls all return
+    the exact-mode logits bit for bit."""
+    import torch
+    from mccnn_b200.engine import (PlannedForward, PipelinedForward, HostForward, PipelinedHostForward, pack_batch)
+    dev = torch.device("cuda:0")
+    B, N, k = 4, 1024, 16
+    fn, store = _make(B, k, 40, dev)
+    host = [make_batch(B, N, "sphere", seed=40 + i) for i in range(5)]
+    devb = [tuple(torch.from_numpy(a).to(dev) for a in h) for h in host]
+    fn(*devb[0])
+    _randomize_store(store)
+    want = [fn(*b)[:B].clone() for b in devb]
+
+    pipe = PipelinedForward(fn, B, depth=3)
+    pipe.calibrate(devb)
+    tickets = []
+    got = [None] * len(devb)
+    for i, b in enumerate(devb):                       # more batches than lanes: lanes are reused
+        if i % 2 == 0:
+            t = pipe.submit(*b)
+        else:
+            t = pipe.submit_packed(pack_batch(*b))
+        out, flag = pipe.result(t)
+        got[i] = out.clone()
+        assert int(flag.item()) == 0
+    for g, w in zip(got, want):
+        assert torch.equal(g, w)
+
+    eng = PlannedForward(fn, B)
+    eng.calibrate(devb)
+    hf = HostForward(eng, dev)
+    cpu = [tuple(torch.from_numpy(a) for a in h) for h in host]
+    for _ in range(2):                                 # first call captures, second replays from pinned staging
+        for c, w in zip(cpu, want):
+            assert torch.equal(hf(*c), w.cpu())
+    blocks = [pack_batch(*c, pin=True) for c in cpu]
+    for blk, w in zip(blocks, want):
+        assert torch.equal(hf.call_packed(blk), w.cpu())
+
+    phf = PipelinedHostForward(pipe, dev)
+    tk = [phf.submit_packed(blk) for blk in blocks[:3]]
+    for t, w in zip(tk, want[:3]):
+        assert torch.equal(phf.result(t), w.cpu())
+
+
 def test_mcclasss_matches_oracle_pipeline():
     import torch
     from oracle import pipeline as OP
