@@ -303,8 +303,9 @@ class PipelinedHostForward:
 
     def submit_packed(self, pinned_block):
         lane = self.pipe._next
-        if self._events[lane] is not None:
-            self._events[lane].synchronize()  # the lane's previous result has reached the host
+        if self._blocks[lane] is not None:
+            raise RuntimeError("PipelinedHostForward: %d results outstanding -- call result() on the oldest ticket "
+                               "before submitting another batch" % self.pipe.depth)
         eng, s = self.pipe.engines[lane], self.pipe.streams[lane]
         if self._result_host[lane] is None:
             self._result_host[lane] = torch.empty(eng._result.shape, dtype=torch.float32).pin_memory()
@@ -322,6 +323,7 @@ class PipelinedHostForward:
 
     def result(self, ticket):
         self._events[ticket].synchronize()
+        self._blocks[ticket] = None
         eng = self.pipe.engines[ticket]
         rows, cols = eng._out_view.shape
         host = self._result_host[ticket]
