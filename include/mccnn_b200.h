@@ -70,6 +70,12 @@ int mc_build_grid(int numPoints, const int* dNumPoints, int batchSize, int numFe
 int mc_sort_features(int numPoints, const int* dNumPoints, int numFeatures, const float* in, const int* newIdx,
                      float* out, void* stream);
 
+/* sort_features of act(in * scale + shift), scale/shift numFeatures floats, relu 0/1: the inference
+ * tf.layers.batch_normalization + tf.nn.relu that precedes a convolution (utils/MCNetworkUtils.py:128-142) folded
+ * into the scatter of tf_ops/sort_gpu.cu:529-540 (no reference counterpart: there it is a separate TF op). */
+int mc_sort_features_affine(int numPoints, const int* dNumPoints, int numFeatures, const float* in, const int* newIdx,
+                            const float* scale, const float* shift, int relu, float* out, void* stream);
+
 /* sortFeaturesBack -- tf_ops/sort_gpu.cc:158-163, tf_ops/sort_gpu.cu:516-527 */
 int mc_sort_features_back(int numPoints, const int* dNumPoints, int numFeatures, const float* in, const int* newIdx,
                           float* out, void* stream);

@@ -36,7 +36,11 @@ def _scheduled(fn):
 
     @functools.wraps(fn)
     def wrapper(*args, **kwargs):
-        return _rt.dispatch([a for a in args if isinstance(a, torch.Tensor)], lambda: fn(*args, **kwargs))
+        if fn.__name__ != "sort_features":  # the one op that folds a pending batch norm into its own kernel
+            args = tuple(_rt.materialize(a) for a in args)
+            kwargs = {k: _rt.materialize(v) for k, v in kwargs.items()}
+        ins = [a.base if isinstance(a, _rt.DeferredAffine) else a for a in list(args) + list(kwargs.values())]
+        return _rt.dispatch([a for a in ins if isinstance(a, torch.Tensor)], lambda: fn(*args, **kwargs))
     return wrapper
 
 
@@ -146,6 +150,9 @@ def sort_features(inFeatures, indexs):
     _req(inFeatures.dim() == 2, "SortFeaturesBackGrad expects features of shape (numPoints, C)")
     _req(indexs.dim() == 1 and indexs.shape[0] == inFeatures.shape[0],
          "SortFeaturesBackGrad expects indexs of shape (numPoints)")
+    if isinstance(inFeatures, _rt.DeferredAffine):  # pending batch norm (+ ReLU): folded into the scatter
+        d = inFeatures
+        return _tag(ops.sort_features(d.base, indexs, _cnt(indexs), affine=(d.scale, d.shift, d.relu)), _cnt(indexs))
     return _tag(ops.sort_features(inFeatures, indexs, _cnt(indexs)), _cnt(indexs))
 
 

@@ -12,7 +12,7 @@ import torch
 
 from . import ops
 from . import variables as _vars
-from .runtime import count_of as _cnt, hint_of as _hint, tag as _tag
+from .runtime import DeferredAffine, count_of as _cnt, hint_of as _hint, materialize as _real, tag as _tag
 
 BN_EPSILON = 1e-3  # tf.layers.batch_normalization default
 
@@ -42,14 +42,36 @@ def _bn_affine(c, training, name, vs):
     return hit[1], hit[2]
 
 
-def _dense(x, w, b, **kw):
+def _dense(x, w, b, pre=None, **kw):
+    """One dense.cu launch.  A pending batch norm (+ ReLU) on the input becomes the layer's prologue; if the layer has
+    a prologue of its own (`pre`, no activation), that second affine is folded into the weights instead:
+    (a * s + t) @ W + b = a @ (s[:, None] * W) + (t @ W + b)."""
+    pre_relu = False
+    if isinstance(x, DeferredAffine):
+        if pre is not None:
+            w, b = _fold_into_weights(pre, w, b)
+        pre, pre_relu, x = (x.scale, x.shift), x.relu, x.base
     nd, h = _cnt(x), _hint(x)
-    return _tag(ops.dense_layer(x, w, b, n_dev=nd, rows_hint=h, **kw), nd, h)
+    return _tag(ops.dense_layer(x, w, b, pre=pre, pre_relu=pre_relu, n_dev=nd, rows_hint=h, **kw), nd, h)
+
+
+_folded = {}
+
+
+def _fold_into_weights(pre, w, b):
+    key = (id(w), id(b))
+    versions = (pre[0]._version, pre[1]._version, w._version, b._version, id(pre[0]), id(pre[1]))
+    hit = _folded.get(key)
+    if hit is None or hit[0] != versions:
+        hit = (versions, (pre[0][:, None] * w).contiguous(), (b + pre[1] @ w).contiguous(), w, b)  # keeps w, b alive
+        _folded[key] = hit
+    return hit[1], hit[2]
 
 
 def _affine_act(x, scale, shift, relu):
-    nd = _cnt(x)
-    return _tag(ops.scale_shift_act(x, scale, shift, relu, nd), nd, _hint(x))
+    """Inference batch norm (+ ReLU): returned as a pending per-column affine that the consumer folds into its own
+    kernel (runtime.DeferredAffine); stacked on another pending one, the inner one is evaluated first."""
+    return DeferredAffine(_real(x), scale, shift, relu)
 
 
 def batch_normalization(inputs, training, name, store=None):

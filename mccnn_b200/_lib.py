@@ -34,6 +34,7 @@ SIGNATURES = {
     "mc_build_grid": (_c_int, [_c_int, _ptr, _c_int, _c_int, _c_int] + [_ptr] * 14),
     "mc_sort_features": (_c_int, [_c_int, _ptr, _c_int, _ptr, _ptr, _ptr, _ptr]),
     "mc_sort_features_back": (_c_int, [_c_int, _ptr, _c_int, _ptr, _ptr, _ptr, _ptr]),
+    "mc_sort_features_affine": (_c_int, [_c_int, _ptr, _c_int, _ptr, _ptr, _ptr, _ptr, _c_int, _ptr, _ptr]),
     "mc_transform_indexs": (_c_int, [_c_int, _ptr, _c_int, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr]),
     "mc_find_neighbors_workspace_ints": (_c_ll, [_c_int]),
     "mc_find_neighbors_count": (_c_int, [_c_int, _c_int, _ptr, _c_int, _c_float, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr,

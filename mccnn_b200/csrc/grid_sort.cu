@@ -137,6 +137,33 @@ void launch_permute_rows(const int* dRows, int capRows, int C, const float* in, 
     }
 }
 
+// out[idx[r], :] = act(in[r, :] * scale + shift): the grid-order scatter of sort_features with a pending inference
+// batch norm (+ ReLU) folded in, so the normalised features are never written in point order
+template <typename VecT>
+__global__ void __launch_bounds__(256) permute_rows_affine_kernel(const int* __restrict__ dRows, int capRows,
+                                                                  int rowVecs, const VecT* __restrict__ in,
+                                                                  const int* __restrict__ idx,
+                                                                  const VecT* __restrict__ scale,
+                                                                  const VecT* __restrict__ shift, int relu,
+                                                                  VecT* __restrict__ out) {
+    const int rows = live_count(dRows, capRows);
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long r = t / rowVecs;
+    if (r >= rows) return;
+    int c = (int)(t - r * rowVecs);
+    VecT v = in[(size_t)r * rowVecs + c];
+    const VecT a = scale[c], b = shift[c];
+    float* pv = reinterpret_cast<float*>(&v);
+    const float* pa = reinterpret_cast<const float*>(&a);
+    const float* pb = reinterpret_cast<const float*>(&b);
+#pragma unroll
+    for (int k = 0; k < (int)(sizeof(VecT) / sizeof(float)); ++k) {
+        float y = fmaf(pv[k], pa[k], pb[k]);
+        pv[k] = relu ? fmaxf(y, 0.f) : y;
+    }
+    out[(size_t)idx[r] * rowVecs + c] = v;
+}
+
 __global__ void __launch_bounds__(kPtThreads) inverse_index_kernel(const int* __restrict__ dN, int cap,
                                                                    const int* __restrict__ newIdx,
                                                                    int* __restrict__ inv) {
@@ -242,6 +269,30 @@ extern "C" int mc_sort_features(int numPoints, const int* dNumPoints, int numFea
                                 const int* newIdx, float* out, void* stream) {
     launch_permute_rows<true>(dNumPoints, numPoints, numFeatures, in, newIdx, out, (cudaStream_t)stream);
     return check_launch("mc_sort_features");
+}
+
+// sort_features of act(in * scale + shift) (scale, shift: numFeatures floats): the inference batch norm + ReLU that
+// precedes a convolution (utils/MCNetworkUtils.py:128-142) folded into the scatter of tf_ops/sort_gpu.cu:529-540
+extern "C" int mc_sort_features_affine(int numPoints, const int* dNumPoints, int numFeatures, const float* in,
+                                       const int* newIdx, const float* scale, const float* shift, int relu,
+                                       float* out, void* stream) {
+    MC_REQUIRE(scale != nullptr && shift != nullptr, "mc_sort_features_affine: scale and shift are required");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (numPoints <= 0 || numFeatures <= 0) return check_launch("mc_sort_features_affine");
+    bool vec4 = (numFeatures % 4 == 0) &&
+                (((uintptr_t)in | (uintptr_t)out | (uintptr_t)scale | (uintptr_t)shift) % 16 == 0);
+    if (vec4) {
+        long long total = (long long)numPoints * (numFeatures / 4);
+        permute_rows_affine_kernel<float4><<<cdiv(total, 256), 256, 0, s>>>(
+            dNumPoints, numPoints, numFeatures / 4, reinterpret_cast<const float4*>(in), newIdx,
+            reinterpret_cast<const float4*>(scale), reinterpret_cast<const float4*>(shift), relu,
+            reinterpret_cast<float4*>(out));
+    } else {
+        long long total = (long long)numPoints * numFeatures;
+        permute_rows_affine_kernel<float><<<cdiv(total, 256), 256, 0, s>>>(dNumPoints, numPoints, numFeatures, in,
+                                                                           newIdx, scale, shift, relu, out);
+    }
+    return check_launch("mc_sort_features_affine");
 }
 
 // sortFeaturesBack, tf_ops/sort_gpu.cu:516-527: out[i,:] = in[newIdx[i],:]

@@ -121,9 +121,15 @@ def build_grid(pts, bids, feats, aabb_min, aabb_max, batch_size, n_cells, violat
     return keys, new_idx, out_pts, out_bids, out_feats, cell_idx
 
 
-def sort_features(feats, new_idx, n_dev=None):
+def sort_features(feats, new_idx, n_dev=None, affine=None):
+    """out[new_idx[i]] = feats[i]; with affine=(scale, shift, relu): out[new_idx[i]] = act(feats[i] * scale + shift)."""
     feats, new_idx = _f(feats), _i(new_idx)
     out = torch.empty_like(feats)
+    if affine is not None:
+        scale, shift, relu = affine
+        check(lib.mc_sort_features_affine(feats.shape[0], _p(n_dev), feats.shape[1], _p(feats), _p(new_idx),
+                                          _p(_f(scale)), _p(_f(shift)), int(bool(relu)), _p(out), _stream()))
+        return out
     check(lib.mc_sort_features(feats.shape[0], _p(n_dev), feats.shape[1], _p(feats), _p(new_idx), _p(out),
                                _stream()))
     return out

@@ -195,3 +195,60 @@ def tag(t, count, hint=None):
 
 def hint_of(t):
     return getattr(t, "_mc_hint", None)
+
+
+class DeferredAffine:
+    """act(base * scale + shift), not computed yet: what an inference batch norm (+ ReLU) returns.
+
+    Every consumer inside this package folds the pending per-column affine into its own kernel -- the prologue of the
+    next dense layer, or the row permutation that brings the features of a convolution into grid order -- so the
+    batch-norm layers of a network cost no launch and no pass over the features.  For anything else the object
+    behaves like the tensor it stands for: torch functions, attribute access and indexing materialise it (one
+    scale_shift_act launch, cached)."""
+
+    def __init__(self, base, scale, shift, relu):
+        self.base, self.scale, self.shift, self.relu = base, scale, shift, bool(relu)
+        self._value = None
+
+    shape = property(lambda self: self.base.shape)
+    dtype = property(lambda self: self.base.dtype)
+    device = property(lambda self: self.base.device)
+    is_cuda = property(lambda self: self.base.is_cuda)
+    _mc_count = property(lambda self: count_of(self.base))
+    _mc_hint = property(lambda self: hint_of(self.base))
+
+    def dim(self):
+        return self.base.dim()
+
+    def materialize(self):
+        if self._value is None:
+            from . import ops
+            nd = count_of(self.base)
+            self._value = dispatch([self.base], lambda: tag(
+                ops.scale_shift_act(self.base, self.scale, self.shift, self.relu, nd), nd, hint_of(self.base)))
+        return self._value
+
+    def __getattr__(self, name):  # only reached for names not defined above
+        if name.startswith("__") or name in ("base", "_value"):
+            raise AttributeError(name)
+        return getattr(self.materialize(), name)
+
+    def __getitem__(self, key):
+        return self.materialize()[key]
+
+    def __len__(self):
+        return self.base.shape[0]
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        def real(a):
+            if isinstance(a, DeferredAffine):
+                return a.materialize()
+            if isinstance(a, (list, tuple)):
+                return type(a)(real(x) for x in a)
+            return a
+        return func(*real(args), **{k: real(v) for k, v in (kwargs or {}).items()})
+
+
+def materialize(t):
+    return t.materialize() if isinstance(t, DeferredAffine) else t

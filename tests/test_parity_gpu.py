@@ -287,3 +287,43 @@ def test_dense_glue_matches_torch(env):
     full = ops.dense_layer(x, w)
     part = ops.dense_layer(x, w, n_dev=cnt)
     assert torch.equal(part[:10], full[:10])
+
+
+def test_deferred_batch_norm_is_folded_exactly(env):
+    """An inference batch norm (+ ReLU) is returned as a pending affine (runtime.DeferredAffine) and folded into its
+    consumer.  The fused scatter (mc_sort_features_affine) equals scale_shift_act followed by sort_features bit for
+    bit; the dense prologue equals the materialised path bit for bit; anything else sees an ordinary tensor."""
+    e = env
+    torch, T = e["torch"], e["T"]
+    from mccnn_b200 import ops, runtime, variables
+    from mccnn_b200 import MCConvModule as M, MCNetworkUtils as U
+    rng = np.random.default_rng(9)
+    for rows, C in ((5400, 128), (387, 256), (33, 7), (1, 4)):
+        x = T(rng.normal(size=(rows, C)).astype(np.float32))
+        s, t = T(rng.uniform(0.5, 1.5, C).astype(np.float32)), T(rng.normal(size=C).astype(np.float32) * 0.1)
+        perm = torch.from_numpy(rng.permutation(rows).astype(np.int32)).to(e["dev"])
+        for relu in (True, False):
+            want = ops.sort_features(ops.scale_shift_act(x, s, t, relu), perm)
+            got = M.sort_features(runtime.DeferredAffine(x, s, t, relu), perm)
+            assert torch.equal(got, want)
+            assert float((want[perm.long()] - (torch.relu(torch.addcmul(t, x, s)) if relu
+                                               else torch.addcmul(t, x, s))).abs().max()) <= 1e-6
+    store = variables.VariableStore(device=e["dev"], seed=1)
+    x = T(rng.normal(size=(300, 64)).astype(np.float32))
+    d = U.batch_norm_RELU_drop_out("bn", x, False, False, 1.0, store)
+    assert isinstance(d, runtime.DeferredAffine) and tuple(d.shape) == (300, 64)
+    for n in ("bn_BN/gamma", "bn_BN/beta", "bn_BN/moving_mean", "bn_BN/moving_variance"):
+        store.vars[n].copy_(T(rng.uniform(0.5, 1.5, 64).astype(np.float32)))
+    d = U.batch_norm_RELU_drop_out("bn", x, False, False, 1.0, store)
+    fused = U.conv_1x1("c", d, 64, 96, store)                       # prologue of the dense layer
+    plain = U.conv_1x1("c", d.materialize(), 64, 96, store)         # separate launch
+    assert torch.equal(fused, plain)
+    g, b = store.vars["bn_BN/gamma"], store.vars["bn_BN/beta"]
+    mu, var = store.vars["bn_BN/moving_mean"], store.vars["bn_BN/moving_variance"]
+    want = torch.relu((x - mu) * torch.rsqrt(var + 1e-3) * g + b)
+    assert float((torch.add(d, 0.0) - want).abs().max()) <= 1e-5    # torch function on the deferred object
+    assert float((d[:5] - want[:5]).abs().max()) <= 1e-5 and d.sum().isfinite()
+    # a second affine in front of a dense layer (the initial batch norm of MLP_2_hidden) is folded into the weights
+    out = U.MLP_2_hidden(d, 64, 32, 16, 10, "head", 1.0, False, store=store)
+    ref = U.MLP_2_hidden(d.materialize(), 64, 32, 16, 10, "head", 1.0, False, store=store)
+    assert float((out - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
