@@ -5,29 +5,40 @@
 // Replaces spatialConvCPU / evaluateMLPKernel / evaluateMLPNoCombinKernel (tf_ops/spatial_conv.cu:24-325,796-871).
 // The reference gives every (pair, MLP block) an 8-thread group that re-reads the block's 176 parameters from
 // global memory, exchanges the hidden activations through shared memory with two CTA-wide barriers, and issues one
-// global float atomicAdd per (pair, neuron).  Here the neighbour list is consumed in its CSR order:
-//   * a WARP owns a run of G consecutive samples and a chunk of 4 MLP blocks (32 neurons).  It walks the run's pair
-//     range in tiles of 64 pairs, TWO pairs per lane, so every lane is busy regardless of how many neighbours a
-//     sample has, and each 128-bit shared-memory broadcast of parameters feeds two pairs;
-//   * the whole block MLP of a pair lives in registers (first layer packed as (w_x, w_y, w_z, b) per neuron);
-//   * the Monte-Carlo sum is a SEGMENTED reduction over the lanes of a tile: for each sample present in the tile the
-//     lanes' contributions are masked and closed with a 31-shuffle reduce-scatter over the chunk's 32 neurons, after
-//     which lane l holds neuron l (one coalesced 128-byte store); partial sums of a sample that continues into the
-//     next tile are carried in a register.  NO atomics, and a summation order that is a pure function of the
-//     neighbour list: bit-reproducible, unlike the reference.
-// FP32 FFMA throughout: parity with the reference is 1e-5 relative, which TF32 tensor-core inputs (10-bit
-// mantissa) cannot meet, and at 8x8 per block the layers are not GEMM-shaped ("why no tensor cores").
+// global float atomicAdd per (pair, neuron).  Here the neighbour list is consumed in its CSR order and the two 8x8
+// layers AND the Monte-Carlo sum run on the tensor cores:
+//
+//   * a WARP owns a run of G <= 16 consecutive samples and a chunk of NB MLP blocks.  It walks the run's pair range
+//     in tiles of 16 pairs (the M of an m16n8k8 MMA); pair records (delta, weight, local sample, neighbour) are
+//     staged 32 at a time -- one pair per lane, coalesced, two loads deep in flight -- through a per-warp
+//     shared-memory slab;
+//   * layer 1 (K = 3) is FFMA and is computed directly in the A-fragment layout of layer 2;
+//   * layer 2:  H2[16 pairs x 8] = H1[16 x 8] . W2^T          one MMA shape, the bias is the C operand;
+//   * layer 3 is evaluated transposed, K3^T[8 neurons x 8 pairs] = Wo . H2^T, so that the C fragment of layer 2 IS the
+//     B fragment of layer 3 (with the k index permuted identically on both operands) and the C fragment of layer 3
+//     IS the B fragment of the reduction -- no shuffles between the layers;
+//   * the Monte-Carlo sum  out[16 samples x 8 neurons] += S[16 x 8 pairs] . V[8 pairs x 8 neurons]  is an MMA with
+//     the 0/1 sample-membership matrix S; the accumulator fragment lives in registers for the whole run and is
+//     stored once.  NO atomics, and a summation order that is a pure function of the neighbour list.
+//
+// Precision: parity with the reference is 1e-5 relative, which single-pass TF32 (10-bit mantissa) cannot meet.  Every
+// product is therefore the 3xTF32 split  a.b ~= a_hi.b_hi + a_lo.b_hi + a_hi.b_lo  (a_hi = tf32(a), a_lo = a - a_hi,
+// FP32 accumulate): ~2^-21 relative per product.  For layer 3 the hi and lo halves of Wo are stacked in the 16 rows
+// of one A operand, so two MMAs per 8 pairs give all four partial products.  S is exact in TF32.
+// Per 16 pairs and block: 11 MMAs (3 + 4 + 4) and ~90 other instructions, against ~370 for the FFMA formulation.
+// (tcgen05 was considered and rejected, DESIGN.md "spatial_conv": the operands are 8x8 per block and change layout
+// between every layer through a ReLU, which would round-trip TMEM <-> registers <-> shared memory four times per
+// tile; the legacy mma.sync path keeps every intermediate in the issuing warp's registers.)
 #include "common.cuh"
+
+#include <cstdlib>
 
 namespace mc {
 namespace {
 
 constexpr int kConvWarps = 4;
-constexpr int kChunkBlocks = 4;                     // MLP blocks per warp
-constexpr int kChunkNeurons = kChunkBlocks * 8;     // 32
-constexpr int kBlockParams = 32 + 8 + 64 + 8 + 64;  // W1p[8][4] (w,b1) | b2[8] | W2[8][8] | bo[8] | Wo[8][8] = 176
-constexpr int kTile = 64;                           // pairs per tile: two per lane
-constexpr int kRadiusTable = 1024;                  // per-cloud 1/r kept in shared memory up to this batch size
+constexpr int kRadiusTable = 1024;  // per-cloud 1/r kept in shared memory up to this batch size
+constexpr int kMaxRun = 16;         // samples per warp: rows of the accumulator fragment
 
 enum ConvMode { kGeneric = 0, kDepthwise = 1, kSingleIn = 2 };
 
@@ -52,250 +63,266 @@ struct ConvArgs {
     float* out;
 };
 
-struct PairState {  // one (neighbour, sample) pair held by a lane
-    float dx, dy, dz;  // (x_j - s_i) / r
-    float invw;        // 1 / (pdf * cnt); 0 for an empty slot
-    int i;             // sample, -1 for an empty slot
-    int j;             // neighbour point
+// D = A(16x8, row) . B(8x8, col) + C, TF32 inputs, FP32 accumulate.  lane = 4g + t:
+//   A: a0 = A[g][t], a1 = A[g+8][t], a2 = A[g][t+4], a3 = A[g+8][t+4];  B: b0 = B[t][g], b1 = B[t+4][g];
+//   C/D: c0 = C[g][2t], c1 = C[g][2t+1], c2 = C[g+8][2t], c3 = C[g+8][2t+1]
+__device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                         uint32_t b0, uint32_t b1, float c0, float c1, float c2, float c3) {
+    asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%12,%13};"
+        : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "f"(c0), "f"(c1), "f"(c2), "f"(c3));
+}
+__device__ __forceinline__ void mma_tf32_acc(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                             uint32_t b0, uint32_t b1) {
+    asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// x = hi + lo (+ 2^-21 |x|): hi is x rounded to TF32 (nearest, ties away), lo the remainder cut to TF32
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi)) & 0xffffe000u;
+}
+
+struct PairLoads {  // second-stage loads of one pair, in flight while the previous 32 pairs are computed
+    float px, py, pz, sx, sy, sz, pdf, f;
+    int lo, hi, bid, i, j;
 };
 
-// 3 -> 8 -> 8 -> 8 block MLP for two pairs at once; parameters from shared memory (broadcast reads)
-__device__ __forceinline__ void block_mlp2(const float4* __restrict__ w, const PairState& a, const PairState& b,
-                                           float (&ka)[8], float (&kb)[8]) {
-    float h1a[8], h1b[8];
-#pragma unroll
-    for (int t = 0; t < 8; ++t) {
-        const float4 p = w[t];
-        h1a[t] = fmaxf(fmaf(a.dx, p.x, fmaf(a.dy, p.y, fmaf(a.dz, p.z, p.w))), 0.0f);
-        h1b[t] = fmaxf(fmaf(b.dx, p.x, fmaf(b.dy, p.y, fmaf(b.dz, p.z, p.w))), 0.0f);
-    }
-    const float4 b2lo = w[8], b2hi = w[9];
-    const float b2[8] = {b2lo.x, b2lo.y, b2lo.z, b2lo.w, b2hi.x, b2hi.y, b2hi.z, b2hi.w};
-    float h2a[8], h2b[8];
-#pragma unroll
-    for (int t = 0; t < 8; ++t) {
-        const float4 p = w[10 + 2 * t], q = w[11 + 2 * t];
-        float sa = b2[t], sb = b2[t];
-        sa = fmaf(h1a[0], p.x, sa); sb = fmaf(h1b[0], p.x, sb);
-        sa = fmaf(h1a[1], p.y, sa); sb = fmaf(h1b[1], p.y, sb);
-        sa = fmaf(h1a[2], p.z, sa); sb = fmaf(h1b[2], p.z, sb);
-        sa = fmaf(h1a[3], p.w, sa); sb = fmaf(h1b[3], p.w, sb);
-        sa = fmaf(h1a[4], q.x, sa); sb = fmaf(h1b[4], q.x, sb);
-        sa = fmaf(h1a[5], q.y, sa); sb = fmaf(h1b[5], q.y, sb);
-        sa = fmaf(h1a[6], q.z, sa); sb = fmaf(h1b[6], q.z, sb);
-        sa = fmaf(h1a[7], q.w, sa); sb = fmaf(h1b[7], q.w, sb);
-        h2a[t] = fmaxf(sa, 0.0f);
-        h2b[t] = fmaxf(sb, 0.0f);
-    }
-    const float4 bolo = w[26], bohi = w[27];
-    const float bo[8] = {bolo.x, bolo.y, bolo.z, bolo.w, bohi.x, bohi.y, bohi.z, bohi.w};
-#pragma unroll
-    for (int t = 0; t < 8; ++t) {
-        const float4 p = w[28 + 2 * t], q = w[29 + 2 * t];
-        float sa = bo[t], sb = bo[t];
-        sa = fmaf(h2a[0], p.x, sa); sb = fmaf(h2b[0], p.x, sb);
-        sa = fmaf(h2a[1], p.y, sa); sb = fmaf(h2b[1], p.y, sb);
-        sa = fmaf(h2a[2], p.z, sa); sb = fmaf(h2b[2], p.z, sb);
-        sa = fmaf(h2a[3], p.w, sa); sb = fmaf(h2b[3], p.w, sb);
-        sa = fmaf(h2a[4], q.x, sa); sb = fmaf(h2b[4], q.x, sb);
-        sa = fmaf(h2a[5], q.y, sa); sb = fmaf(h2b[5], q.y, sb);
-        sa = fmaf(h2a[6], q.z, sa); sb = fmaf(h2b[6], q.z, sb);
-        sa = fmaf(h2a[7], q.w, sa); sb = fmaf(h2b[7], q.w, sb);
-        ka[t] = sa;
-        kb[t] = sb;
-    }
-}
-
-// one butterfly level of the reduce-scatter over the 32 lanes: lanes with bit OFF set keep the upper half of the
-// live values.  After levels 16, 8, 4, 2, 1 lane l holds the warp total of value index l.
-template <int OFF>
-__device__ __forceinline__ void reduce_scatter_step(float (&v)[kChunkNeurons], int lane) {
-    const bool upper = (lane & OFF) != 0;
-#pragma unroll
-    for (int k = 0; k < OFF; ++k) {
-        const float send = upper ? v[k] : v[k + OFF];
-        const float keep = upper ? v[k + OFF] : v[k];
-        v[k] = keep + __shfl_xor_sync(MC_FULL_MASK, send, OFF);
-    }
-}
-
-template <int MODE>
+template <int MODE, int NB>
 __global__ void __launch_bounds__(kConvWarps * 32) spatial_conv_kernel(const ConvArgs a) {
-    __shared__ __align__(16) float sW[kChunkBlocks * kBlockParams];
     __shared__ float sInvR[kRadiusTable];
-    const int chunk = blockIdx.y;
-    const int lane = lane_id();
+    __shared__ __align__(16) float4 sDelta[kConvWarps][2][32];  // (dx, dy, dz, -) of the staged pairs
+    __shared__ __align__(8) float sWgt[kConvWarps][2][32];      // 1 / (pdf * cnt)  [x feature, single-input mode]
+    __shared__ __align__(8) int sLocal[kConvWarps][2][32];      // sample - first sample of the run; -1 = empty slot
+    __shared__ __align__(8) int sNeigh[kConvWarps][2][32];      // neighbour point (row of the feature matrix)
 
-    // stage this chunk's parameters (zero for blocks past the end) and the per-cloud 1/r
-    for (int t = threadIdx.x; t < kChunkBlocks * kBlockParams; t += blockDim.x) {
-        const int q = t / kBlockParams, e = t - q * kBlockParams;
-        const int blk = chunk * kChunkBlocks + q;
-        float v = 0.0f;
-        if (blk < a.numBlocks) {
-            const int nr0 = blk * 8;
-            if (e < 32) {
-                const int tt = e >> 2, c = e & 3;
-                v = c < 3 ? a.W1[(nr0 + tt) * 3 + c] : a.b1[nr0 + tt];
-            } else if (e < 40) {
-                v = a.b2[nr0 + e - 32];
-            } else if (e < 104) {
-                v = a.W2[blk * 64 + e - 40];
-            } else if (e < 112) {
-                v = a.bo[nr0 + e - 104];
-            } else {
-                v = a.Wo[blk * 64 + e - 112];
-            }
-        }
-        sW[t] = v;
-    }
+    // the chunk's parameters in fragment order, pre-split for the 3xTF32 products: five 128-bit words per
+    // (block, lane), lane-contiguous so that every read in the tile loop is one conflict-free LDS.128
+    __shared__ __align__(16) float4 sFrag[NB][5][32];
+
     const bool radiusTable = a.B <= kRadiusTable;
-    if (radiusTable)
+    if (radiusTable) {
         for (int b = threadIdx.x; b < a.B; b += blockDim.x) {
             const float r = a.scaleInv ? a.radius * max_extent(a.mn, a.mx, b) : a.radius;
             sInvR[b] = 1.0f / r;
         }
+    }
+    const int blk0 = blockIdx.y * NB;
+    // flat reference layouts: W1[(8q+u)*3+axis], b1[8q+u], W2[q*64 + out*8 + in], b2[8q+out], Wo[(8q+out)*8 + in],
+    // bo[8q+out]
+    for (int idx = threadIdx.x; idx < NB * 32; idx += blockDim.x) {
+        const int q = idx >> 5, ln = idx & 31, fg = ln >> 2, ft = ln & 3;
+        const int blk = blk0 + q;
+        float4 f0 = make_float4(0.f, 0.f, 0.f, 0.f), f1 = f0, f2 = f0, f3 = f0, f4 = f0;
+        if (blk < a.numBlocks) {
+            const int u0 = blk * 8 + ft, u1 = u0 + 4;
+            // layer 1, hidden units t and t+4: (w_x, w_y, w_z, bias)
+            f0 = make_float4(a.W1[u0 * 3], a.W1[u0 * 3 + 1], a.W1[u0 * 3 + 2], a.b1[u0]);
+            f1 = make_float4(a.W1[u1 * 3], a.W1[u1 * 3 + 1], a.W1[u1 * 3 + 2], a.b1[u1]);
+            // layer 2 B fragment: W2[out g][in t], W2[out g][in t+4] as (hi0, hi1, lo0, lo1)
+            uint32_t h0, l0, h1, l1;
+            split_tf32(a.W2[blk * 64 + fg * 8 + ft], h0, l0);
+            split_tf32(a.W2[blk * 64 + fg * 8 + ft + 4], h1, l1);
+            f2 = make_float4(__uint_as_float(h0), __uint_as_float(h1), __uint_as_float(l0), __uint_as_float(l1));
+            // layer 3 A fragment: rows 0-7 hi(Wo), rows 8-15 lo(Wo); k' = t <-> in 2t, k' = t+4 <-> in 2t+1 (the
+            // order the layer-2 C fragment holds its columns in)
+            split_tf32(a.Wo[(blk * 8 + fg) * 8 + 2 * ft], h0, l0);
+            split_tf32(a.Wo[(blk * 8 + fg) * 8 + 2 * ft + 1], h1, l1);
+            f3 = make_float4(__uint_as_float(h0), __uint_as_float(l0), __uint_as_float(h1), __uint_as_float(l1));
+            // layer 2 bias of outputs 2t, 2t+1 | layer 3 bias of neuron g | feature column weighing neuron g
+            const int fc = (MODE == kGeneric) ? (blk * 8 + fg) % a.C : min(blk * 8 + fg, a.C - 1);
+            f4 = make_float4(a.b2[blk * 8 + 2 * ft], a.b2[blk * 8 + 2 * ft + 1], a.bo[blk * 8 + fg],
+                             __int_as_float(fc));
+        }
+        sFrag[q][0][ln] = f0;
+        sFrag[q][1][ln] = f1;
+        sFrag[q][2][ln] = f2;
+        sFrag[q][3][ln] = f3;
+        sFrag[q][4][ln] = f4;
+    }
     __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = lane_id();
+    const int g = lane >> 2, t = lane & 3;
 
     const int M = live_count(a.dM, a.capM);
     const int K = live_count(a.dK, a.capK);
-    const int s0 = (blockIdx.x * kConvWarps + (threadIdx.x >> 5)) * a.G;  // first sample of this warp's run
+    const int s0 = (blockIdx.x * kConvWarps + warp) * a.G;  // first sample of this warp's run
     if (s0 >= a.capM) return;
-    const int n = chunk * kChunkNeurons + lane;  // neuron this lane zero-fills
-
-    // samples without neighbours (and capacity padding rows) get a defined zero output
-    const int sEndCap = min(s0 + a.G, a.capM);
-    for (int s = s0; s < sEndCap; ++s) {
-        bool empty = s >= M;
-        if (!empty) {
-            const int lo = a.start[s];
-            const int hi = min((s < M - 1) ? a.start[s + 1] : K, K);
-            empty = hi <= lo;
-        }
-        if (empty && n < a.nOut) a.out[(size_t)s * a.outStride + n] = 0.0f;
-    }
-    if (s0 >= M) return;
+    const int rowsOut = min(a.G, a.capM - s0);  // rows written: live samples and capacity padding (zeros)
     const int s1 = min(s0 + a.G, M);
-    const int P0 = min(a.start[s0], K);
-    const int P1 = min((s1 < M) ? a.start[s1] : K, K);
+    int P0 = 0, P1 = 0;
+    if (s0 < M) {
+        P0 = min(a.start[s0], K);
+        P1 = min((s1 < M) ? a.start[s1] : K, K);
+    }
 
-    float carry = 0.0f;   // partial sum (neuron n) of the sample that continues from the previous tile
-    int openSample = -1;  // that sample
-
-    for (int tile = P0; tile < P1; tile += kTile) {
-        PairState ps[2];
-        int hiOf[2];
+    float acc[NB][4];  // out[s0 + {g, g+8}][8 blk + {2t, 2t+1}]
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const int p = tile + u * 32 + lane;
-            ps[u].i = -1;
-            ps[u].j = 0;
-            ps[u].dx = ps[u].dy = ps[u].dz = ps[u].invw = 0.0f;
-            hiOf[u] = 0;
-            if (p < P1) {
-                const int2 pr = a.pairs[p];
-                const int j = pr.x, i = pr.y;
-                float invR;
-                if (radiusTable) {
-                    invR = sInvR[a.bids[j]];
-                } else {
-                    const float ext = max_extent(a.mn, a.mx, a.bids[j]);
-                    invR = 1.0f / (a.scaleInv ? a.radius * ext : a.radius);
-                }
-                const int lo = a.start[i];
-                const int hi = min((i < M - 1) ? a.start[i + 1] : K, K);
-                const float cnt = a.avg ? (float)(hi - lo) : 1.0f;
-                ps[u].i = i;
-                ps[u].j = j;
-                ps[u].dx = (a.pts[(size_t)j * 3] - a.samples[(size_t)i * 3]) * invR;
-                ps[u].dy = (a.pts[(size_t)j * 3 + 1] - a.samples[(size_t)i * 3 + 1]) * invR;
-                ps[u].dz = (a.pts[(size_t)j * 3 + 2] - a.samples[(size_t)i * 3 + 2]) * invR;
-                ps[u].invw = 1.0f / (a.pdfs[p] * cnt);
-                hiOf[u] = hi;
-            }
+    for (int q = 0; q < NB; ++q) acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.f;
+
+    // ---- pair staging, two loads deep: (A) pair + pdf of batch k+2, (B) geometry of batch k+1, compute batch k
+    int2 prA = make_int2(0, -1);
+    float pdfA = 1.0f;
+    auto load_a = [&](int p) {
+        const bool ok = p < P1;
+        prA = ok ? a.pairs[p] : make_int2(0, -1);
+        pdfA = ok ? a.pdfs[p] : 1.0f;
+    };
+    auto load_b = [&]() {
+        PairLoads L;
+        L.j = prA.x;
+        L.i = prA.y;
+        L.pdf = pdfA;
+        const int j = L.j, i = max(L.i, 0);
+        L.px = a.pts[(size_t)j * 3];
+        L.py = a.pts[(size_t)j * 3 + 1];
+        L.pz = a.pts[(size_t)j * 3 + 2];
+        L.sx = a.samples[(size_t)i * 3];
+        L.sy = a.samples[(size_t)i * 3 + 1];
+        L.sz = a.samples[(size_t)i * 3 + 2];
+        L.bid = a.bids[j];
+        L.lo = a.start[i];
+        L.hi = (i < M - 1) ? a.start[i + 1] : K;
+        L.f = (MODE == kSingleIn) ? a.feats[j] : 1.0f;
+        return L;
+    };
+    auto stage = [&](const PairLoads& L, int buf) {
+        float invR;
+        if (radiusTable) {
+            invR = sInvR[L.bid];
+        } else {
+            const float ext = max_extent(a.mn, a.mx, L.bid);
+            invR = 1.0f / (a.scaleInv ? a.radius * ext : a.radius);
         }
-        // samples present in the tile: consecutive ids iFirst..iLast (pairs are CSR-ordered by sample)
-        const int iFirst = __shfl_sync(MC_FULL_MASK, ps[0].i, 0);
-        const int lastSlot = min(tile + kTile, P1) - 1 - tile;
-        const int iLast = __shfl_sync(MC_FULL_MASK, lastSlot >= 32 ? ps[1].i : ps[0].i, lastSlot & 31);
-        const int hiLast = __shfl_sync(MC_FULL_MASK, lastSlot >= 32 ? hiOf[1] : hiOf[0], lastSlot & 31);
-        const bool lastComplete = hiLast <= tile + kTile;  // does sample iLast end inside this tile?
-        float fs[2] = {0.f, 0.f};
-        if (MODE == kSingleIn) {
-#pragma unroll
-            for (int u = 0; u < 2; ++u)
-                if (ps[u].i >= 0) fs[u] = a.feats[ps[u].j] * ps[u].invw;
-        }
+        const bool ok = L.i >= 0;
+        const float cnt = a.avg ? (float)(min(L.hi, K) - L.lo) : 1.0f;
+        const float invw = ok ? L.f / (L.pdf * cnt) : 0.0f;
+        sDelta[warp][buf][lane] = ok ? make_float4((L.px - L.sx) * invR, (L.py - L.sy) * invR, (L.pz - L.sz) * invR, 0.f)
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+        sWgt[warp][buf][lane] = invw;
+        sLocal[warp][buf][lane] = ok ? L.i - s0 : -1;
+        sNeigh[warp][buf][lane] = ok ? L.j : 0;
+    };
 
-        float va[kChunkNeurons], vb[kChunkNeurons];  // f * kappa / (pdf * cnt) of this lane's two pairs
+    const int nBatches = (P1 - P0 + 31) >> 5;
+    if (nBatches > 0) {
+        load_a(P0 + lane);
+        PairLoads L = load_b();
+        load_a(P0 + 32 + lane);
+        stage(L, 0);
+        __syncwarp();
+    }
+    for (int k = 0; k < nBatches; ++k) {
+        const int buf = k & 1;
+        PairLoads L;
+        const bool more = k + 1 < nBatches;
+        if (more) {
+            L = load_b();
+            load_a(P0 + (k + 2) * 32 + lane);
+        }
+        const int left = P1 - (P0 + k * 32);  // pairs in this batch (may exceed 32)
 #pragma unroll
-        for (int q = 0; q < kChunkBlocks; ++q) {
-            const int blk = chunk * kChunkBlocks + q;
-            if (blk >= a.numBlocks) {  // warp-uniform
-#pragma unroll
-                for (int t = 0; t < 8; ++t) va[q * 8 + t] = vb[q * 8 + t] = 0.0f;
-                continue;
-            }
-            // parameters are re-read from shared memory (128-bit broadcasts) for every tile; the empty asm keeps the
-            // compiler from hoisting the loop-invariant loads into registers (it spills otherwise)
-            int wOff = q * kBlockParams;
-            asm volatile("" : "+r"(wOff));
-            float ka[8], kb[8];
-            block_mlp2(reinterpret_cast<const float4*>(sW + wOff), ps[0], ps[1], ka, kb);
-            // weight each kernel value by the pair's feature / (pdf * cnt)
+        for (int h = 0; h < 2; ++h) {
+            if (h * 16 >= left) break;  // warp-uniform
+            const int r0 = h * 16;
+            const float4 da = sDelta[warp][buf][r0 + g], db = sDelta[warp][buf][r0 + g + 8];
+            // pairs this lane holds as COLUMNS of the transposed fragments: rows 2t, 2t+1 (first 8) and 8+2t, 8+2t+1
+            const float2 wA = *reinterpret_cast<const float2*>(&sWgt[warp][buf][r0 + 2 * t]);
+            const float2 wB = *reinterpret_cast<const float2*>(&sWgt[warp][buf][r0 + 8 + 2 * t]);
+            const int2 lA = *reinterpret_cast<const int2*>(&sLocal[warp][buf][r0 + 2 * t]);
+            const int2 lB = *reinterpret_cast<const int2*>(&sLocal[warp][buf][r0 + 8 + 2 * t]);
+            // membership matrix S[sample row][pair column] as A fragments (exact in TF32)
+            const uint32_t one = 0x3f800000u;
+            const uint32_t sA0 = lA.x == g ? one : 0u, sA1 = lA.x == g + 8 ? one : 0u;
+            const uint32_t sA2 = lA.y == g ? one : 0u, sA3 = lA.y == g + 8 ? one : 0u;
+            const uint32_t sB0 = lB.x == g ? one : 0u, sB1 = lB.x == g + 8 ? one : 0u;
+            const uint32_t sB2 = lB.y == g ? one : 0u, sB3 = lB.y == g + 8 ? one : 0u;
+            float fA0[NB], fA1[NB], fB0[NB], fB1[NB];  // feature x weight of the four column pairs, per block
             if (MODE == kSingleIn) {
 #pragma unroll
-                for (int t = 0; t < 8; ++t) {
-                    va[q * 8 + t] = ka[t] * fs[0];
-                    vb[q * 8 + t] = kb[t] * fs[1];
-                }
+                for (int q = 0; q < NB; ++q) { fA0[q] = wA.x; fA1[q] = wA.y; fB0[q] = wB.x; fB1[q] = wB.y; }
             } else {
+                const int2 jA = *reinterpret_cast<const int2*>(&sNeigh[warp][buf][r0 + 2 * t]);
+                const int2 jB = *reinterpret_cast<const int2*>(&sNeigh[warp][buf][r0 + 8 + 2 * t]);
 #pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                    if (ps[u].i >= 0) {
-                        const float* frow = a.feats + (size_t)ps[u].j * a.C;
-                        if (MODE == kDepthwise) {
-                            const float4 f0 = *reinterpret_cast<const float4*>(frow + blk * 8);
-                            const float4 f1 = *reinterpret_cast<const float4*>(frow + blk * 8 + 4);
-                            f[0] = f0.x; f[1] = f0.y; f[2] = f0.z; f[3] = f0.w;
-                            f[4] = f1.x; f[5] = f1.y; f[6] = f1.z; f[7] = f1.w;
-                        } else {
-#pragma unroll
-                            for (int t = 0; t < 8; ++t) f[t] = frow[(blk * 8 + t) % a.C];
-                        }
-                    }
-#pragma unroll
-                    for (int t = 0; t < 8; ++t) {
-                        if (u == 0)
-                            va[q * 8 + t] = ka[t] * (f[t] * ps[0].invw);
-                        else
-                            vb[q * 8 + t] = kb[t] * (f[t] * ps[1].invw);
-                    }
+                for (int q = 0; q < NB; ++q) {
+                    const int fcol = __float_as_int(sFrag[q][4][lane].w);
+                    fA0[q] = a.feats[(size_t)jA.x * a.C + fcol] * wA.x;
+                    fA1[q] = a.feats[(size_t)jA.y * a.C + fcol] * wA.y;
+                    fB0[q] = a.feats[(size_t)jB.x * a.C + fcol] * wB.x;
+                    fB1[q] = a.feats[(size_t)jB.y * a.C + fcol] * wB.y;
                 }
             }
-        }
-        // segmented sum over the samples of the tile: mask, then one 31-shuffle reduce-scatter over the 32 neurons of
-        // the chunk (independent shuffles per butterfly level), after which lane l holds neuron chunk*32 + l
-        for (int cur = iFirst; cur <= iLast; ++cur) {
-            const bool m0 = ps[0].i == cur, m1 = ps[1].i == cur;
-            if (__ballot_sync(MC_FULL_MASK, m0 || m1) == 0u) continue;  // sample without pairs
-            float w[kChunkNeurons];
 #pragma unroll
-            for (int t = 0; t < kChunkNeurons; ++t) w[t] = (m0 ? va[t] : 0.0f) + (m1 ? vb[t] : 0.0f);
-            reduce_scatter_step<16>(w, lane);
-            reduce_scatter_step<8>(w, lane);
-            reduce_scatter_step<4>(w, lane);
-            reduce_scatter_step<2>(w, lane);
-            reduce_scatter_step<1>(w, lane);
-            float tot = w[0];
-            if (cur == openSample) tot += carry;
-            if (cur < iLast || lastComplete) {
-                if (n < a.nOut) a.out[(size_t)cur * a.outStride + n] = tot;  // one coalesced 128-byte store per warp
-            } else {
-                carry = tot;  // the sample continues in the next tile
+            for (int q = 0; q < NB; ++q) {
+                if (blk0 + q >= a.numBlocks) break;  // warp-uniform
+                // parameters are re-read from shared memory for every tile; the empty asm keeps the compiler from
+                // hoisting the loop-invariant loads into (far too many) registers
+                int fo = q * 5 * 32 + lane;
+                asm volatile("" : "+r"(fo));
+                const float4* frag = &sFrag[0][0][0] + fo;
+                const float4 wa = frag[0], wb = frag[32], p2 = frag[64], p3 = frag[96], p4 = frag[128];
+                const uint32_t w2h[2] = {__float_as_uint(p2.x), __float_as_uint(p2.y)};
+                const uint32_t w2l[2] = {__float_as_uint(p2.z), __float_as_uint(p2.w)};
+                const uint32_t w3[4] = {__float_as_uint(p3.x), __float_as_uint(p3.y), __float_as_uint(p3.z),
+                                        __float_as_uint(p3.w)};
+                const float c2[2] = {p4.x, p4.y};
+                const float c3 = p4.z;
+                // layer 1 in the A-fragment layout of layer 2: hidden t / t+4 of pairs g / g+8
+                uint32_t h1h[4], h1l[4];
+                split_tf32(fmaxf(fmaf(da.x, wa.x, fmaf(da.y, wa.y, fmaf(da.z, wa.z, wa.w))), 0.f), h1h[0], h1l[0]);
+                split_tf32(fmaxf(fmaf(db.x, wa.x, fmaf(db.y, wa.y, fmaf(db.z, wa.z, wa.w))), 0.f), h1h[1], h1l[1]);
+                split_tf32(fmaxf(fmaf(da.x, wb.x, fmaf(da.y, wb.y, fmaf(da.z, wb.z, wb.w))), 0.f), h1h[2], h1l[2]);
+                split_tf32(fmaxf(fmaf(db.x, wb.x, fmaf(db.y, wb.y, fmaf(db.z, wb.z, wb.w))), 0.f), h1h[3], h1l[3]);
+                // layer 2: small terms first
+                float d2[4];
+                mma_tf32(d2, h1l[0], h1l[1], h1l[2], h1l[3], w2h[0], w2h[1], c2[0], c2[1], c2[0],
+                         c2[1]);
+                mma_tf32_acc(d2, h1h[0], h1h[1], h1h[2], h1h[3], w2l[0], w2l[1]);
+                mma_tf32_acc(d2, h1h[0], h1h[1], h1h[2], h1h[3], w2h[0], w2h[1]);
+                uint32_t h2h[4], h2l[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) split_tf32(fmaxf(d2[e], 0.f), h2h[e], h2l[e]);
+                // layer 3, transposed: rows = neuron g (hi part of Wo) / neuron g (lo part), columns = 8 pairs
+                float d3a[4], d3b[4];
+                mma_tf32(d3a, w3[0], w3[1], w3[2], w3[3], h2l[0], h2l[1], c3, c3, 0.f, 0.f);
+                mma_tf32(d3b, w3[0], w3[1], w3[2], w3[3], h2l[2], h2l[3], c3, c3, 0.f, 0.f);
+                mma_tf32_acc(d3a, w3[0], w3[1], w3[2], w3[3], h2h[0], h2h[1]);
+                mma_tf32_acc(d3b, w3[0], w3[1], w3[2], w3[3], h2h[2], h2h[3]);
+                // kernel value x feature / (pdf * cnt): neuron g of pairs 2t, 2t+1 | 8+2t, 8+2t+1
+                uint32_t vh[4], vl[4];
+                split_tf32((d3a[0] + d3a[2]) * fA0[q], vh[0], vl[0]);
+                split_tf32((d3a[1] + d3a[3]) * fA1[q], vh[1], vl[1]);
+                split_tf32((d3b[0] + d3b[2]) * fB0[q], vh[2], vl[2]);
+                split_tf32((d3b[1] + d3b[3]) * fB1[q], vh[3], vl[3]);
+                // Monte-Carlo sum over the pairs of each sample of the run
+                mma_tf32_acc(acc[q], sA0, sA1, sA2, sA3, vl[0], vl[1]);
+                mma_tf32_acc(acc[q], sB0, sB1, sB2, sB3, vl[2], vl[3]);
+                mma_tf32_acc(acc[q], sA0, sA1, sA2, sA3, vh[0], vh[1]);
+                mma_tf32_acc(acc[q], sB0, sB1, sB2, sB3, vh[2], vh[3]);
             }
         }
-        openSample = lastComplete ? -1 : iLast;
+        if (more) stage(L, buf ^ 1);
+        __syncwarp();
+    }
+
+    // ---- store: lane (g, t) holds samples s0+g, s0+g+8 x neurons 8 blk + {2t, 2t+1}.  Samples without neighbours
+    // and the capacity-padding rows past the live count get their defined zeros here as well.
+#pragma unroll
+    for (int q = 0; q < NB; ++q) {
+        const int n = (blk0 + q) * 8 + 2 * t;
+        if (blk0 + q >= a.numBlocks) break;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int row = g + 8 * half;
+            if (row < rowsOut) {
+                float* o = a.out + (size_t)(s0 + row) * a.outStride + n;
+                if (n < a.nOut) o[0] = acc[q][2 * half];
+                if (n + 1 < a.nOut) o[1] = acc[q][2 * half + 1];
+            }
+        }
     }
 }
 
@@ -309,6 +336,13 @@ __global__ void __launch_bounds__(256) combine_kernel(const int* __restrict__ dM
     float acc = 0.0f;
     for (int c = 0; c < C; ++c) acc += s[c];
     out[t] = acc;
+}
+
+constexpr int kChunkBlocks = 4;  // MLP blocks per warp
+
+int env_int(const char* name, int dflt) {
+    const char* v = std::getenv(name);
+    return v ? std::atoi(v) : dflt;
 }
 
 }  // namespace
@@ -347,12 +381,14 @@ extern "C" int mc_spatial_conv(int avg, int scaleInv, int numNeighbors, const in
     const int nOut = combin ? C * numOutFeatures : C;
     const int nb = (nOut + 7) / 8;
     const int chunks = cdiv(nb, kChunkBlocks);
-    // run length per warp: ~3 tiles of pairs per warp (the partially filled last tile stays cheap) -- but the op is
-    // latency bound, so never at the price of leaving the GPU short of warps
+    // run length per warp: ~8 tiles of 16 pairs (the partially filled last tile stays cheap), at most the 16 rows of
+    // the accumulator fragment -- but the op is latency bound, so never at the price of leaving the GPU short of warps
+    static const int forcedG = env_int("MCCNN_CONV_RUN", 0);  // tuning knob (samples per warp), 0 = heuristic
     long long avgK = numNeighbors / (long long)numSamples;
-    int G = (int)(192 / (avgK > 0 ? avgK : 1));
-    G = G < 1 ? 1 : (G > 16 ? 16 : G);
-    while (G > 1 && (long long)cdiv(numSamples, G) * chunks < 2048) --G;
+    int G = (int)(128 / (avgK > 0 ? avgK : 1));
+    G = G < 1 ? 1 : (G > kMaxRun ? kMaxRun : G);
+    while (G > 1 && (long long)cdiv(numSamples, G) * chunks < 1776) --G;
+    if (forcedG > 0) G = forcedG > kMaxRun ? kMaxRun : forcedG;
     ConvArgs a;
     a.avg = avg != 0;
     a.scaleInv = scaleInv != 0;
@@ -382,22 +418,21 @@ extern "C" int mc_spatial_conv(int avg, int scaleInv, int numNeighbors, const in
     a.bo = bout;
     dim3 grid(cdiv(cdiv(numSamples, G), kConvWarps), chunks);
     if (!combin) {
-        MC_REQUIRE(((uintptr_t)features) % 16 == 0, "mc_spatial_conv: feature buffer must be 16-byte aligned");
         a.nOut = nOut;
         a.outStride = C;
         a.out = outFeatures;
-        spatial_conv_kernel<kDepthwise><<<grid, kConvWarps * 32, 0, s>>>(a);
+        spatial_conv_kernel<kDepthwise, kChunkBlocks><<<grid, kConvWarps * 32, 0, s>>>(a);
     } else if (C == 1) {
         a.nOut = nOut;
         a.outStride = numOutFeatures;
         a.out = outFeatures;
-        spatial_conv_kernel<kSingleIn><<<grid, kConvWarps * 32, 0, s>>>(a);
+        spatial_conv_kernel<kSingleIn, kChunkBlocks><<<grid, kConvWarps * 32, 0, s>>>(a);
     } else {
         MC_REQUIRE(workspace != nullptr, "mc_spatial_conv: workspace required for multi-feature convolutions");
         a.nOut = nb * 8;
         a.outStride = nb * 8;
         a.out = workspace;
-        spatial_conv_kernel<kGeneric><<<grid, kConvWarps * 32, 0, s>>>(a);
+        spatial_conv_kernel<kGeneric, kChunkBlocks><<<grid, kConvWarps * 32, 0, s>>>(a);
         long long total = (long long)numSamples * numOutFeatures;
         combine_kernel<<<cdiv(total, 256), 256, 0, s>>>(dNumSamples, numSamples, C, numOutFeatures, nb * 8, workspace,
                                                         outFeatures);
