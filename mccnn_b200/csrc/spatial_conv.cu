@@ -25,7 +25,8 @@
 // product is therefore the 3xTF32 split  a.b ~= a_hi.b_hi + a_lo.b_hi + a_hi.b_lo  (a_hi = tf32(a), a_lo = a - a_hi,
 // FP32 accumulate): ~2^-21 relative per product.  For layer 3 the hi and lo halves of Wo are stacked in the 16 rows
 // of one A operand, so two MMAs per 8 pairs give all four partial products.  S is exact in TF32.
-// Per 16 pairs and block: 11 MMAs (3 + 4 + 4) and ~90 other instructions, against ~370 for the FFMA formulation.
+// Per 16 pairs and block: 11 MMAs (3 + 4 + 4), or 8 in the single-input mode where the linear last layer is applied
+// after the sum, and ~70-90 other instructions, against ~370 for the FFMA formulation.
 // (tcgen05 was considered and rejected, DESIGN.md "spatial_conv": the operands are 8x8 per block and change layout
 // between every layer through a ReLU, which would round-trip TMEM <-> registers <-> shared memory four times per
 // tile; the legacy mma.sync path keeps every intermediate in the issuing warp's registers.)
@@ -79,10 +80,11 @@ __device__ __forceinline__ void mma_tf32_acc(float (&d)[4], uint32_t a0, uint32_
         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-// x = hi + lo (+ 2^-21 |x|): hi is x rounded to TF32 (nearest, ties away), lo the remainder cut to TF32
+// x = hi + lo (+ 2^-21 |x|): hi is x rounded to TF32 (nearest, ties away); lo is the exact remainder, of which the
+// tensor core reads the upper 19 bits
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
     hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
-    lo = __float_as_uint(x - __uint_as_float(hi)) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
 }
 
 struct PairLoads {  // second-stage loads of one pair, in flight while the previous 32 pairs are computed
@@ -90,6 +92,15 @@ struct PairLoads {  // second-stage loads of one pair, in flight while the previ
     int lo, hi, bid, i, j;
 };
 
+__device__ __forceinline__ float layer1(const float4& d, const float4& w) {
+    return fmaxf(fmaf(d.x, w.x, fmaf(d.y, w.y, fmaf(d.z, w.z, w.w))), 0.f);
+}
+
+// MODE kGeneric / kDepthwise: every neuron has its own feature weight, all three layers are evaluated per pair.
+// MODE kSingleIn (one input feature, the first convolution of every network): the weight f_p / (pdf_p cnt) does not
+// depend on the neuron and the last layer is linear, so it is applied AFTER the Monte-Carlo sum:
+//     out[i,n] = sum_u Wo[n,u] . Z[i,u] + bo[n] . F[i],   Z[i,u] = sum_p w_p H2[p,u],   F[i] = sum_p w_p
+// which removes layer 3 from the per-pair work (8 instead of 11 MMAs per 16 pairs and block).
 template <int MODE, int NB>
 __global__ void __launch_bounds__(kConvWarps * 32) spatial_conv_kernel(const ConvArgs a) {
     __shared__ float sInvR[kRadiusTable];
@@ -121,20 +132,26 @@ __global__ void __launch_bounds__(kConvWarps * 32) spatial_conv_kernel(const Con
             // layer 1, hidden units t and t+4: (w_x, w_y, w_z, bias)
             f0 = make_float4(a.W1[u0 * 3], a.W1[u0 * 3 + 1], a.W1[u0 * 3 + 2], a.b1[u0]);
             f1 = make_float4(a.W1[u1 * 3], a.W1[u1 * 3 + 1], a.W1[u1 * 3 + 2], a.b1[u1]);
-            // layer 2 B fragment: W2[out g][in t], W2[out g][in t+4] as (hi0, hi1, lo0, lo1)
             uint32_t h0, l0, h1, l1;
             split_tf32(a.W2[blk * 64 + fg * 8 + ft], h0, l0);
             split_tf32(a.W2[blk * 64 + fg * 8 + ft + 4], h1, l1);
-            f2 = make_float4(__uint_as_float(h0), __uint_as_float(h1), __uint_as_float(l0), __uint_as_float(l1));
-            // layer 3 A fragment: rows 0-7 hi(Wo), rows 8-15 lo(Wo); k' = t <-> in 2t, k' = t+4 <-> in 2t+1 (the
-            // order the layer-2 C fragment holds its columns in)
+            if (MODE == kSingleIn)  // layer 2 as A fragment (transposed layer): rows 0-7 hi(W2), rows 8-15 lo(W2)
+                f2 = make_float4(__uint_as_float(h0), __uint_as_float(l0), __uint_as_float(h1), __uint_as_float(l1));
+            else  // layer 2 as B fragment: W2[out g][in t], W2[out g][in t+4] as (hi0, hi1, lo0, lo1)
+                f2 = make_float4(__uint_as_float(h0), __uint_as_float(h1), __uint_as_float(l0), __uint_as_float(l1));
+            // layer 3: Wo[out g][in 2t], Wo[out g][in 2t+1] as (hi0, lo0, hi1, lo1).  A fragment of the transposed
+            // layer (rows 0-7 hi, rows 8-15 lo; k' = t <-> in 2t, k' = t+4 <-> in 2t+1: the order the layer-2 C
+            // fragment holds its columns in), or B fragment of the post-sum projection of the single-input mode
             split_tf32(a.Wo[(blk * 8 + fg) * 8 + 2 * ft], h0, l0);
             split_tf32(a.Wo[(blk * 8 + fg) * 8 + 2 * ft + 1], h1, l1);
             f3 = make_float4(__uint_as_float(h0), __uint_as_float(l0), __uint_as_float(h1), __uint_as_float(l1));
-            // layer 2 bias of outputs 2t, 2t+1 | layer 3 bias of neuron g | feature column weighing neuron g
-            const int fc = (MODE == kGeneric) ? (blk * 8 + fg) % a.C : min(blk * 8 + fg, a.C - 1);
-            f4 = make_float4(a.b2[blk * 8 + 2 * ft], a.b2[blk * 8 + 2 * ft + 1], a.bo[blk * 8 + fg],
-                             __int_as_float(fc));
+            if (MODE == kSingleIn) {  // layer 2 bias of unit g | layer 3 bias of neurons 2t, 2t+1
+                f4 = make_float4(a.b2[blk * 8 + fg], a.bo[blk * 8 + 2 * ft], a.bo[blk * 8 + 2 * ft + 1], 0.f);
+            } else {  // layer 2 bias of units 2t, 2t+1 | layer 3 bias of neuron g | feature column of neuron g
+                const int fc = (MODE == kGeneric) ? (blk * 8 + fg) % a.C : min(blk * 8 + fg, a.C - 1);
+                f4 = make_float4(a.b2[blk * 8 + 2 * ft], a.b2[blk * 8 + 2 * ft + 1], a.bo[blk * 8 + fg],
+                                 __int_as_float(fc));
+            }
         }
         sFrag[q][0][ln] = f0;
         sFrag[q][1][ln] = f1;
@@ -158,7 +175,10 @@ __global__ void __launch_bounds__(kConvWarps * 32) spatial_conv_kernel(const Con
         P1 = min((s1 < M) ? a.start[s1] : K, K);
     }
 
-    float acc[NB][4];  // out[s0 + {g, g+8}][8 blk + {2t, 2t+1}]
+    // accumulator fragments, rows = samples s0 + {g, g+8}: out[.][8 blk + {2t, 2t+1}], or (single-input mode)
+    // Z[.][unit {2t, 2t+1}] and the weight sums F[.]
+    float acc[NB][4];
+    float accF[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int q = 0; q < NB; ++q) acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.f;
 
@@ -203,7 +223,7 @@ __global__ void __launch_bounds__(kConvWarps * 32) spatial_conv_kernel(const Con
                                      : make_float4(0.f, 0.f, 0.f, 0.f);
         sWgt[warp][buf][lane] = invw;
         sLocal[warp][buf][lane] = ok ? L.i - s0 : -1;
-        sNeigh[warp][buf][lane] = ok ? L.j : 0;
+        if (MODE != kSingleIn) sNeigh[warp][buf][lane] = ok ? L.j : 0;
     };
 
     const int nBatches = (P1 - P0 + 31) >> 5;
@@ -239,13 +259,58 @@ __global__ void __launch_bounds__(kConvWarps * 32) spatial_conv_kernel(const Con
             const uint32_t sA2 = lA.y == g ? one : 0u, sA3 = lA.y == g + 8 ? one : 0u;
             const uint32_t sB0 = lB.x == g ? one : 0u, sB1 = lB.x == g + 8 ? one : 0u;
             const uint32_t sB2 = lB.y == g ? one : 0u, sB3 = lB.y == g + 8 ? one : 0u;
-            float fA0[NB], fA1[NB], fB0[NB], fB1[NB];  // feature x weight of the four column pairs, per block
-            if (MODE == kSingleIn) {
+
+            if constexpr (MODE == kSingleIn) {
+                {  // F[i] += sum of the weights of sample i's pairs (every column of the fragment holds the same sum)
+                    uint32_t fh[4], fl[4];
+                    split_tf32(wA.x, fh[0], fl[0]);
+                    split_tf32(wA.y, fh[1], fl[1]);
+                    split_tf32(wB.x, fh[2], fl[2]);
+                    split_tf32(wB.y, fh[3], fl[3]);
+                    mma_tf32_acc(accF, sA0, sA1, sA2, sA3, fl[0], fl[1]);
+                    mma_tf32_acc(accF, sB0, sB1, sB2, sB3, fl[2], fl[3]);
+                    mma_tf32_acc(accF, sA0, sA1, sA2, sA3, fh[0], fh[1]);
+                    mma_tf32_acc(accF, sB0, sB1, sB2, sB3, fh[2], fh[3]);
+                }
 #pragma unroll
-                for (int q = 0; q < NB; ++q) { fA0[q] = wA.x; fA1[q] = wA.y; fB0[q] = wB.x; fB1[q] = wB.y; }
+                for (int q = 0; q < NB; ++q) {
+                    // parameters are re-read from shared memory for every tile; the empty asm keeps the compiler from
+                    // hoisting the loop-invariant loads into (far too many) registers
+                    int fo = q * 5 * 32 + lane;
+                    asm volatile("" : "+r"(fo));
+                    const float4* frag = &sFrag[0][0][0] + fo;
+                    const float4 wa = frag[0], wb = frag[32], p2 = frag[64];
+                    const float b2g = frag[128].x;
+                    const uint32_t a20 = __float_as_uint(p2.x), a21 = __float_as_uint(p2.y);
+                    const uint32_t a22 = __float_as_uint(p2.z), a23 = __float_as_uint(p2.w);
+                    // layer 1 as B fragments of the transposed layer 2: units t / t+4 of pair g (first / second 8)
+                    uint32_t xh[4], xl[4];
+                    split_tf32(layer1(da, wa), xh[0], xl[0]);
+                    split_tf32(layer1(da, wb), xh[1], xl[1]);
+                    split_tf32(layer1(db, wa), xh[2], xl[2]);
+                    split_tf32(layer1(db, wb), xh[3], xl[3]);
+                    // layer 2, transposed: rows = unit g (hi part of W2) / unit g (lo part), columns = 8 pairs
+                    float d2a[4], d2b[4];
+                    mma_tf32(d2a, a20, a21, a22, a23, xl[0], xl[1], b2g, b2g, 0.f, 0.f);
+                    mma_tf32(d2b, a20, a21, a22, a23, xl[2], xl[3], b2g, b2g, 0.f, 0.f);
+                    mma_tf32_acc(d2a, a20, a21, a22, a23, xh[0], xh[1]);
+                    mma_tf32_acc(d2b, a20, a21, a22, a23, xh[2], xh[3]);
+                    // w_p . H2[p][unit g] of pairs 2t, 2t+1 | 8+2t, 8+2t+1
+                    uint32_t vh[4], vl[4];
+                    split_tf32(fmaxf(d2a[0] + d2a[2], 0.f) * wA.x, vh[0], vl[0]);
+                    split_tf32(fmaxf(d2a[1] + d2a[3], 0.f) * wA.y, vh[1], vl[1]);
+                    split_tf32(fmaxf(d2b[0] + d2b[2], 0.f) * wB.x, vh[2], vl[2]);
+                    split_tf32(fmaxf(d2b[1] + d2b[3], 0.f) * wB.y, vh[3], vl[3]);
+                    // Z[i][u] += sum over the pairs of sample i
+                    mma_tf32_acc(acc[q], sA0, sA1, sA2, sA3, vl[0], vl[1]);
+                    mma_tf32_acc(acc[q], sB0, sB1, sB2, sB3, vl[2], vl[3]);
+                    mma_tf32_acc(acc[q], sA0, sA1, sA2, sA3, vh[0], vh[1]);
+                    mma_tf32_acc(acc[q], sB0, sB1, sB2, sB3, vh[2], vh[3]);
+                }
             } else {
                 const int2 jA = *reinterpret_cast<const int2*>(&sNeigh[warp][buf][r0 + 2 * t]);
                 const int2 jB = *reinterpret_cast<const int2*>(&sNeigh[warp][buf][r0 + 8 + 2 * t]);
+                float fA0[NB], fA1[NB], fB0[NB], fB1[NB];  // feature x weight of the four column pairs, per block
 #pragma unroll
                 for (int q = 0; q < NB; ++q) {
                     const int fcol = __float_as_int(sFrag[q][4][lane].w);
@@ -254,54 +319,48 @@ __global__ void __launch_bounds__(kConvWarps * 32) spatial_conv_kernel(const Con
                     fB0[q] = a.feats[(size_t)jB.x * a.C + fcol] * wB.x;
                     fB1[q] = a.feats[(size_t)jB.y * a.C + fcol] * wB.y;
                 }
-            }
 #pragma unroll
-            for (int q = 0; q < NB; ++q) {
-                if (blk0 + q >= a.numBlocks) break;  // warp-uniform
-                // parameters are re-read from shared memory for every tile; the empty asm keeps the compiler from
-                // hoisting the loop-invariant loads into (far too many) registers
-                int fo = q * 5 * 32 + lane;
-                asm volatile("" : "+r"(fo));
-                const float4* frag = &sFrag[0][0][0] + fo;
-                const float4 wa = frag[0], wb = frag[32], p2 = frag[64], p3 = frag[96], p4 = frag[128];
-                const uint32_t w2h[2] = {__float_as_uint(p2.x), __float_as_uint(p2.y)};
-                const uint32_t w2l[2] = {__float_as_uint(p2.z), __float_as_uint(p2.w)};
-                const uint32_t w3[4] = {__float_as_uint(p3.x), __float_as_uint(p3.y), __float_as_uint(p3.z),
-                                        __float_as_uint(p3.w)};
-                const float c2[2] = {p4.x, p4.y};
-                const float c3 = p4.z;
-                // layer 1 in the A-fragment layout of layer 2: hidden t / t+4 of pairs g / g+8
-                uint32_t h1h[4], h1l[4];
-                split_tf32(fmaxf(fmaf(da.x, wa.x, fmaf(da.y, wa.y, fmaf(da.z, wa.z, wa.w))), 0.f), h1h[0], h1l[0]);
-                split_tf32(fmaxf(fmaf(db.x, wa.x, fmaf(db.y, wa.y, fmaf(db.z, wa.z, wa.w))), 0.f), h1h[1], h1l[1]);
-                split_tf32(fmaxf(fmaf(da.x, wb.x, fmaf(da.y, wb.y, fmaf(da.z, wb.z, wb.w))), 0.f), h1h[2], h1l[2]);
-                split_tf32(fmaxf(fmaf(db.x, wb.x, fmaf(db.y, wb.y, fmaf(db.z, wb.z, wb.w))), 0.f), h1h[3], h1l[3]);
-                // layer 2: small terms first
-                float d2[4];
-                mma_tf32(d2, h1l[0], h1l[1], h1l[2], h1l[3], w2h[0], w2h[1], c2[0], c2[1], c2[0],
-                         c2[1]);
-                mma_tf32_acc(d2, h1h[0], h1h[1], h1h[2], h1h[3], w2l[0], w2l[1]);
-                mma_tf32_acc(d2, h1h[0], h1h[1], h1h[2], h1h[3], w2h[0], w2h[1]);
-                uint32_t h2h[4], h2l[4];
+                for (int q = 0; q < NB; ++q) {
+                    int fo = q * 5 * 32 + lane;
+                    asm volatile("" : "+r"(fo));
+                    const float4* frag = &sFrag[0][0][0] + fo;
+                    const float4 wa = frag[0], wb = frag[32], p2 = frag[64], p3 = frag[96], p4 = frag[128];
+                    const uint32_t w2h0 = __float_as_uint(p2.x), w2h1 = __float_as_uint(p2.y);
+                    const uint32_t w2l0 = __float_as_uint(p2.z), w2l1 = __float_as_uint(p2.w);
+                    const uint32_t w30 = __float_as_uint(p3.x), w31 = __float_as_uint(p3.y);
+                    const uint32_t w32 = __float_as_uint(p3.z), w33 = __float_as_uint(p3.w);
+                    // layer 1 in the A-fragment layout of layer 2: hidden t / t+4 of pairs g / g+8
+                    uint32_t h1h[4], h1l[4];
+                    split_tf32(layer1(da, wa), h1h[0], h1l[0]);
+                    split_tf32(layer1(db, wa), h1h[1], h1l[1]);
+                    split_tf32(layer1(da, wb), h1h[2], h1l[2]);
+                    split_tf32(layer1(db, wb), h1h[3], h1l[3]);
+                    // layer 2: small terms first
+                    float d2[4];
+                    mma_tf32(d2, h1l[0], h1l[1], h1l[2], h1l[3], w2h0, w2h1, p4.x, p4.y, p4.x, p4.y);
+                    mma_tf32_acc(d2, h1h[0], h1h[1], h1h[2], h1h[3], w2l0, w2l1);
+                    mma_tf32_acc(d2, h1h[0], h1h[1], h1h[2], h1h[3], w2h0, w2h1);
+                    uint32_t h2h[4], h2l[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) split_tf32(fmaxf(d2[e], 0.f), h2h[e], h2l[e]);
-                // layer 3, transposed: rows = neuron g (hi part of Wo) / neuron g (lo part), columns = 8 pairs
-                float d3a[4], d3b[4];
-                mma_tf32(d3a, w3[0], w3[1], w3[2], w3[3], h2l[0], h2l[1], c3, c3, 0.f, 0.f);
-                mma_tf32(d3b, w3[0], w3[1], w3[2], w3[3], h2l[2], h2l[3], c3, c3, 0.f, 0.f);
-                mma_tf32_acc(d3a, w3[0], w3[1], w3[2], w3[3], h2h[0], h2h[1]);
-                mma_tf32_acc(d3b, w3[0], w3[1], w3[2], w3[3], h2h[2], h2h[3]);
-                // kernel value x feature / (pdf * cnt): neuron g of pairs 2t, 2t+1 | 8+2t, 8+2t+1
-                uint32_t vh[4], vl[4];
-                split_tf32((d3a[0] + d3a[2]) * fA0[q], vh[0], vl[0]);
-                split_tf32((d3a[1] + d3a[3]) * fA1[q], vh[1], vl[1]);
-                split_tf32((d3b[0] + d3b[2]) * fB0[q], vh[2], vl[2]);
-                split_tf32((d3b[1] + d3b[3]) * fB1[q], vh[3], vl[3]);
-                // Monte-Carlo sum over the pairs of each sample of the run
-                mma_tf32_acc(acc[q], sA0, sA1, sA2, sA3, vl[0], vl[1]);
-                mma_tf32_acc(acc[q], sB0, sB1, sB2, sB3, vl[2], vl[3]);
-                mma_tf32_acc(acc[q], sA0, sA1, sA2, sA3, vh[0], vh[1]);
-                mma_tf32_acc(acc[q], sB0, sB1, sB2, sB3, vh[2], vh[3]);
+                    for (int e = 0; e < 4; ++e) split_tf32(fmaxf(d2[e], 0.f), h2h[e], h2l[e]);
+                    // layer 3, transposed: rows = neuron g (hi part of Wo) / neuron g (lo part), columns = 8 pairs
+                    float d3a[4], d3b[4];
+                    mma_tf32(d3a, w30, w31, w32, w33, h2l[0], h2l[1], p4.z, p4.z, 0.f, 0.f);
+                    mma_tf32(d3b, w30, w31, w32, w33, h2l[2], h2l[3], p4.z, p4.z, 0.f, 0.f);
+                    mma_tf32_acc(d3a, w30, w31, w32, w33, h2h[0], h2h[1]);
+                    mma_tf32_acc(d3b, w30, w31, w32, w33, h2h[2], h2h[3]);
+                    // kernel value x feature / (pdf * cnt): neuron g of pairs 2t, 2t+1 | 8+2t, 8+2t+1
+                    uint32_t vh[4], vl[4];
+                    split_tf32((d3a[0] + d3a[2]) * fA0[q], vh[0], vl[0]);
+                    split_tf32((d3a[1] + d3a[3]) * fA1[q], vh[1], vl[1]);
+                    split_tf32((d3b[0] + d3b[2]) * fB0[q], vh[2], vl[2]);
+                    split_tf32((d3b[1] + d3b[3]) * fB1[q], vh[3], vl[3]);
+                    // Monte-Carlo sum over the pairs of each sample of the run
+                    mma_tf32_acc(acc[q], sA0, sA1, sA2, sA3, vl[0], vl[1]);
+                    mma_tf32_acc(acc[q], sB0, sB1, sB2, sB3, vl[2], vl[3]);
+                    mma_tf32_acc(acc[q], sA0, sA1, sA2, sA3, vh[0], vh[1]);
+                    mma_tf32_acc(acc[q], sB0, sB1, sB2, sB3, vh[2], vh[3]);
+                }
             }
         }
         if (more) stage(L, buf ^ 1);
@@ -314,13 +373,28 @@ __global__ void __launch_bounds__(kConvWarps * 32) spatial_conv_kernel(const Con
     for (int q = 0; q < NB; ++q) {
         const int n = (blk0 + q) * 8 + 2 * t;
         if (blk0 + q >= a.numBlocks) break;
+        float o4[4] = {acc[q][0], acc[q][1], acc[q][2], acc[q][3]};
+        if constexpr (MODE == kSingleIn) {
+            // out[i][n] = sum_u Z[i][u] Wo[n][u] + bo[n] F[i]: the accumulator fragment is the A fragment (its columns
+            // 2t, 2t+1 are k' = t, t+4), the pre-split Wo slice the B fragment
+            const float4 p3 = sFrag[q][3][lane], p4 = sFrag[q][4][lane];
+            uint32_t zh[4], zl[4];
+            split_tf32(acc[q][0], zh[0], zl[0]);
+            split_tf32(acc[q][2], zh[1], zl[1]);
+            split_tf32(acc[q][1], zh[2], zl[2]);
+            split_tf32(acc[q][3], zh[3], zl[3]);
+            mma_tf32(o4, zl[0], zl[1], zl[2], zl[3], __float_as_uint(p3.x), __float_as_uint(p3.z), p4.y * accF[0],
+                     p4.z * accF[0], p4.y * accF[2], p4.z * accF[2]);
+            mma_tf32_acc(o4, zh[0], zh[1], zh[2], zh[3], __float_as_uint(p3.y), __float_as_uint(p3.w));
+            mma_tf32_acc(o4, zh[0], zh[1], zh[2], zh[3], __float_as_uint(p3.x), __float_as_uint(p3.z));
+        }
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
             const int row = g + 8 * half;
             if (row < rowsOut) {
                 float* o = a.out + (size_t)(s0 + row) * a.outStride + n;
-                if (n < a.nOut) o[0] = acc[q][2 * half];
-                if (n + 1 < a.nOut) o[1] = acc[q][2 * half + 1];
+                if (n < a.nOut) o[0] = o4[2 * half];
+                if (n + 1 < a.nOut) o[1] = o4[2 * half + 1];
             }
         }
     }
@@ -338,7 +412,24 @@ __global__ void __launch_bounds__(256) combine_kernel(const int* __restrict__ dM
     out[t] = acc;
 }
 
-constexpr int kChunkBlocks = 4;  // MLP blocks per warp
+constexpr int kChunkBlocks = 4;  // MLP blocks per warp (fewer when the convolution has fewer)
+
+// blocks past the end of the parameter arrays are evaluated with zero parameters (no branch in the tile loop, so the
+// compiler interleaves the blocks' MMA chains); the chunk width is matched to small convolutions instead
+template <int MODE>
+void launch_conv(const ConvArgs& a, int nb, int G, cudaStream_t s) {
+    const int runs = cdiv(a.capM, G);
+    if (nb >= 3) {
+        dim3 grid(cdiv(runs, kConvWarps), cdiv(nb, 4));
+        spatial_conv_kernel<MODE, 4><<<grid, kConvWarps * 32, 0, s>>>(a);
+    } else if (nb == 2) {
+        dim3 grid(cdiv(runs, kConvWarps), 1);
+        spatial_conv_kernel<MODE, 2><<<grid, kConvWarps * 32, 0, s>>>(a);
+    } else {
+        dim3 grid(cdiv(runs, kConvWarps), 1);
+        spatial_conv_kernel<MODE, 1><<<grid, kConvWarps * 32, 0, s>>>(a);
+    }
+}
 
 int env_int(const char* name, int dflt) {
     const char* v = std::getenv(name);
@@ -416,23 +507,22 @@ extern "C" int mc_spatial_conv(int avg, int scaleInv, int numNeighbors, const in
     a.b2 = b2;
     a.Wo = Wout;
     a.bo = bout;
-    dim3 grid(cdiv(cdiv(numSamples, G), kConvWarps), chunks);
     if (!combin) {
         a.nOut = nOut;
         a.outStride = C;
         a.out = outFeatures;
-        spatial_conv_kernel<kDepthwise, kChunkBlocks><<<grid, kConvWarps * 32, 0, s>>>(a);
+        launch_conv<kDepthwise>(a, nb, G, s);
     } else if (C == 1) {
         a.nOut = nOut;
         a.outStride = numOutFeatures;
         a.out = outFeatures;
-        spatial_conv_kernel<kSingleIn, kChunkBlocks><<<grid, kConvWarps * 32, 0, s>>>(a);
+        launch_conv<kSingleIn>(a, nb, G, s);
     } else {
         MC_REQUIRE(workspace != nullptr, "mc_spatial_conv: workspace required for multi-feature convolutions");
         a.nOut = nb * 8;
         a.outStride = nb * 8;
         a.out = workspace;
-        spatial_conv_kernel<kGeneric, kChunkBlocks><<<grid, kConvWarps * 32, 0, s>>>(a);
+        launch_conv<kGeneric>(a, nb, G, s);
         long long total = (long long)numSamples * numOutFeatures;
         combine_kernel<<<cdiv(total, 256), 256, 0, s>>>(dNumSamples, numSamples, C, numOutFeatures, nb * 8, workspace,
                                                         outFeatures);
