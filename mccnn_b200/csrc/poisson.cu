@@ -67,6 +67,10 @@ struct CloudCtx {
         y = p[1];
         z = p[2];
     }
+    // accepted points so far, per cell, compacted in place: the a-th accepted point of cell c is the point
+    // cLo + sAccIdx[cell(c).x - cLo + a], a < sAccCnt[c]  (only when points and cell rows are staged; else nullptr)
+    unsigned short* sAccIdx;
+    unsigned char* sAccCnt;
     unsigned char* sFlags;        // shared-memory flags (index: sorted position - cLo) or nullptr
     unsigned char* gFlags;        // global flags (index: sorted position) when the cloud does not fit
     int cLo;
@@ -85,38 +89,59 @@ struct CloudCtx {
 };
 
 // one cell of the current phase, processed by one warp
-__device__ __forceinline__ void process_cell(const CloudCtx& cx, SelShared& sh, int warp, int lane, int x, int y, int z,
-                                             int2 own, int ph) {
+__device__ __forceinline__ void process_cell(const CloudCtx& cx, SelShared& sh, int warp, int lane, int cellId, int x,
+                                             int y, int z, int2 own, int ph) {
     const int n = cx.n;
     const unsigned ltMask = (1u << lane) - 1u;
-    // ---- A: compact the accepted points of the 26 neighbour cells into the warp's list
-    int nlo = 0, nhi = 0;
+    // ---- A: gather the accepted points of the 26 neighbour cells into the warp's list
+    int nlo = 0, nhi = 0, ncell = -1;
     if (lane < 27 && lane != kSelfOffset) {
         int qx = x + cx.offX, qy = y + cx.offY, qz = z + cx.offZ;
         if (qx >= 0 && qx < n && qy >= 0 && qy < n && qz >= 0 && qz < n) {
-            int2 ce = cx.cell((qx * n + qy) * n + qz);
+            ncell = (qx * n + qy) * n + qz;
+            int2 ce = cx.cell(ncell);
             nlo = ce.x;
             nhi = ce.y;
         }
     }
-    if (lane == 0) sh.listCount[warp] = 0;
-    __syncwarp();
-    for (int j = nlo; j < nhi; ++j)
-        if (cx.flag(j)) {
-            int slot = atomicAdd(&sh.listCount[warp], 1);
-            if (slot < kListCap) sh.listIdx[warp][slot] = j;
+    int L;
+    bool listOk;
+    if (cx.sAccIdx != nullptr) {
+        // per-cell accepted lists: a lane copies the (few) accepted points of its neighbour cell, placed by a warp scan
+        const int cntL = ncell >= 0 ? cx.sAccCnt[ncell] : 0;
+        const int incl = warp_inclusive_scan(cntL);
+        L = __shfl_sync(MC_FULL_MASK, incl, 31);
+        listOk = L <= kListCap;
+        if (listOk) {
+            const int pos = incl - cntL;
+            for (int k = 0; k < cntL; ++k) {
+                float qx, qy, qz;
+                cx.point(cx.cLo + cx.sAccIdx[nlo - cx.cLo + k], qx, qy, qz);
+                sh.list[warp][pos + k] = make_float4(qx, qy, qz, 0.f);
+            }
         }
-    __syncwarp();
-    int L = sh.listCount[warp];
-    bool listOk = L <= kListCap;  // else: fall back to walking the cells directly (never wrong, only slow)
-    if (listOk) {
-        for (int t = lane; t < L; t += 32) {
-            float qx, qy, qz;
-            cx.point(sh.listIdx[warp][t], qx, qy, qz);
-            sh.list[warp][t] = make_float4(qx, qy, qz, 0.f);
+    } else {
+        // no staging (very large clouds): compact through the accepted flags
+        if (lane == 0) sh.listCount[warp] = 0;
+        __syncwarp();
+        for (int j = nlo; j < nhi; ++j)
+            if (cx.flag(j)) {
+                int slot = atomicAdd(&sh.listCount[warp], 1);
+                if (slot < kListCap) sh.listIdx[warp][slot] = j;
+            }
+        __syncwarp();
+        L = sh.listCount[warp];
+        listOk = L <= kListCap;  // else: fall back to walking the cells directly (never wrong, only slow)
+        if (listOk) {
+            for (int t = lane; t < L; t += 32) {
+                float qx, qy, qz;
+                cx.point(sh.listIdx[warp][t], qx, qy, qz);
+                sh.list[warp][t] = make_float4(qx, qy, qz, 0.f);
+            }
         }
     }
     __syncwarp();
+    int accOwn = 0;  // accepted points of this cell so far
 
     // ---- B + C: own points, 32 at a time
     for (int c0 = own.x; c0 < own.y; c0 += 32) {
@@ -168,8 +193,13 @@ __device__ __forceinline__ void process_cell(const CloudCtx& cx, SelShared& sh, 
             if (lane == u) mySel = (any == 0);
         }
         if (holder && mySel) cx.set_flag(i, (unsigned char)(ph + 1));
+        const unsigned selMask = __ballot_sync(MC_FULL_MASK, holder && mySel);
+        if (cx.sAccIdx != nullptr) {
+            if (holder && mySel)
+                cx.sAccIdx[own.x - cx.cLo + accOwn + __popc(selMask & ltMask)] = (unsigned short)(i - cx.cLo);
+            accOwn += __popc(selMask);
+        }
         if (c0 + 32 < own.y && listOk) {  // later chunks of this cell must see this chunk's accepted points
-            const unsigned selMask = __ballot_sync(MC_FULL_MASK, holder && mySel);
             const int pos = L + __popc(selMask & ltMask);
             if (holder && mySel && pos < kListCap) sh.list[warp][pos] = make_float4(px, py, pz, 0.f);
             L += __popc(selMask);
@@ -177,6 +207,7 @@ __device__ __forceinline__ void process_cell(const CloudCtx& cx, SelShared& sh, 
         }
         __syncwarp();
     }
+    if (cx.sAccIdx != nullptr && lane == 0) cx.sAccCnt[cellId] = (unsigned char)min(accOwn, 255);
 }
 
 __global__ void __launch_bounds__(kSelThreads)
@@ -191,6 +222,8 @@ __global__ void __launch_bounds__(kSelThreads)
     unsigned short* cellList = reinterpret_cast<unsigned short*>(sFlags + kSelFlagBytes);
     int2* sCells = reinterpret_cast<int2*>(sFlags + kSelFlagBytes + kCellListCap * sizeof(unsigned short));
     float* sPts = reinterpret_cast<float*>(sCells + kStageCells);
+    unsigned short* sAccIdx = reinterpret_cast<unsigned short*>(sPts + kStagePts * 3);
+    unsigned char* sAccCnt = reinterpret_cast<unsigned char*>(sAccIdx + kStagePts);
     const int lane = lane_id(), warp = threadIdx.x >> 5;
     const unsigned ltMask = (1u << lane) - 1u;
 
@@ -218,7 +251,10 @@ __global__ void __launch_bounds__(kSelThreads)
         int lo = INT_MAX, hi = 0;
         for (int c = threadIdx.x; c < cellsPerCloud; c += kSelThreads) {
             int2 ce = cells[c];
-            if (stageCells) sCells[c] = ce;
+            if (stageCells) {
+                sCells[c] = ce;
+                sAccCnt[c] = 0;
+            }
             if (ce.y > ce.x) {
                 lo = min(lo, ce.x);
                 hi = max(hi, ce.y);
@@ -273,6 +309,8 @@ __global__ void __launch_bounds__(kSelThreads)
     cx.pts = pts;
     cx.sPts = stagePts ? sPts : nullptr;
     cx.sFlags = inSmem ? sFlags : nullptr;
+    cx.sAccIdx = (stagePts && stageCells) ? sAccIdx : nullptr;
+    cx.sAccCnt = sAccCnt;
     cx.gFlags = selGlobal;
     cx.cLo = cLo;
     cx.n = n;
@@ -284,14 +322,17 @@ __global__ void __launch_bounds__(kSelThreads)
         cx.thr = exact_radius_threshold(scaleInv ? __fmul_rn(radius, ext) : radius);
     }
 
+    const float invN = 1.0f / (float)n, invNN = 1.0f / (float)(n * n);
     if (nCloud > 0) {
         for (int ph = 0; ph < 27; ++ph) {
             if (useLists) {
                 const int beg = sh.phaseCellStart[ph], end = sh.phaseCellStart[ph + 1];
                 for (int t = beg + warp; t < end; t += kSelWarps) {
                     const int c = cellList[t];
-                    const int x = c / (n * n), y = (c / n) % n, z = c % n;
-                    process_cell(cx, sh, warp, lane, x, y, z, cx.cell(c), ph);
+                    // c < 8192: exact in float, cheaper than three integer divisions on the serial path
+                    const int x = (int)(((float)c + 0.5f) * invNN), rem = c - x * n * n;
+                    const int y = (int)(((float)rem + 0.5f) * invN), z = rem - y * n;
+                    process_cell(cx, sh, warp, lane, c, x, y, z, cx.cell(c), ph);
                 }
                 if (end == beg) continue;  // nothing was written in this phase: no barrier needed (uniform)
             } else {
@@ -305,7 +346,7 @@ __global__ void __launch_bounds__(kSelThreads)
                     const int x = tx * 3 + 1 + ox, y = ty * 3 + 1 + oy, z = tz * 3 + 1 + oz;
                     const int2 own = cx.cell((x * n + y) * n + z);
                     if (own.y <= own.x) continue;
-                    process_cell(cx, sh, warp, lane, x, y, z, own, ph);
+                    process_cell(cx, sh, warp, lane, (x * n + y) * n + z, x, y, z, own, ph);
                 }
             }
             __syncthreads();
@@ -377,7 +418,8 @@ __global__ void __launch_bounds__(kSelThreads)
 }
 
 constexpr size_t kSelSmemBytes = sizeof(SelShared) + kSelFlagBytes + kCellListCap * sizeof(unsigned short) +
-                                 kStageCells * sizeof(int2) + kStagePts * 3 * sizeof(float);
+                                 kStageCells * sizeof(int2) + kStagePts * 3 * sizeof(float) +
+                                 kStagePts * sizeof(unsigned short) + kStageCells;
 
 }  // namespace
 }  // namespace mc
