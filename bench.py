@@ -125,10 +125,12 @@ def algorithmic_bytes(op, call, sizes, B, k, n_in=1):
         return N[call + 1] * (4 + 8 * feat_c[call])
     if op == "transform_indexs":
         return 8 * N[call] + 8 * N[call + 1]
-    if op == "dense_layer":                          # Reduce_1, Reduce_2, then the three layers of the head
-        rows, kin, nout = [(N[1], k, 2 * k), (N[2], 2 * k, 4 * k), (B, 4 * k, 2 * k), (B, 2 * k, k),
-                           (B, k, NUM_CAT)][call]
+    if op == "dense_layer":                          # Reduce_1, Reduce_2
+        rows, kin, nout = [(N[1], k, 2 * k), (N[2], 2 * k, 4 * k)][call]
         return 4 * (rows * kin + kin * nout + rows * nout + 2 * kin + 3 * nout)
+    if op == "mlp_rows":                             # the three layers of the head in one launch
+        w = [4 * k, 2 * k, k, NUM_CAT]
+        return 4 * (B * w[0] + B * w[3] + sum(a * b + 3 * b for a, b in zip(w[:-1], w[1:])) + 2 * w[0])
     if op in ("find_neighbors_count", "find_neighbors_pack", "find_neighbors", "find_neighbors_fused"):
         M, Np, G = N[call + 1], N[call], B * conv_n[call] ** 3
         full = 16 * M + 12 * Np + 8 * min(G, 27 * M) + 4 * M + 8 * K[call]
@@ -272,7 +274,7 @@ def run_ours(args, rank, world, dev):
     launches_per_forward = int(lib.mc_launch_count() - c0)
     names = ["compute_aabb", "build_grid", "sort_points_step1", "sort_points_step2", "sort_features",
              "transform_indexs", "find_neighbors_count", "find_neighbors_pack", "find_neighbors_fused", "compute_pdf",
-             "poisson_sampling", "get_sampled_features", "spatial_conv", "dense_layer", "scale_shift_act"]
+             "poisson_sampling", "get_sampled_features", "spatial_conv", "dense_layer", "mlp_rows", "scale_shift_act"]
     orig = {n: getattr(ops, n) for n in names}
     events = []
 

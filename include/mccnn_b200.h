@@ -153,6 +153,14 @@ int mc_dense_layer(int numRows, const int* dNumRows, int numRowsHint, int K, int
                    const float* t1, int relu1, const float* W, const float* bias, const float* s2, const float* t2,
                    int relu2, float* y, void* stream);
 
+/* A whole MLP on few rows in ONE launch -- MLP_1_hidden / MLP_2_hidden, utils/MCNetworkUtils.py:20-107:
+ *   a_0 = act0(x * s0 + t0);  a_{l+1} = act_l((a_l @ W[l] + bias[l]) * scale[l] + shift[l]);  y = a_numLayers.
+ * dims: numLayers + 1 host ints (each 1..1024); W / bias / scale / shift: host arrays of numLayers device pointers
+ * (bias and scale+shift may be NULL per layer); relu: numLayers host flags.  One CTA per row: meant for <= ~128 rows. */
+int mc_mlp_rows(int numRows, const int* dNumRows, int numLayers, const int* dims, const float* x, const float* s0,
+                const float* t0, int relu0, const float* const* W, const float* const* bias,
+                const float* const* scale, const float* const* shift, const int* relu, float* y, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -55,6 +55,28 @@ def _dense(x, w, b, pre=None, **kw):
     return _tag(ops.dense_layer(x, w, b, pre=pre, pre_relu=pre_relu, n_dev=nd, rows_hint=h, **kw), nd, h)
 
 
+def _mlp(x, layers, pre=None):
+    """The classification heads: few rows (one per cloud), so the whole MLP is ONE dense.cu launch (mc_mlp_rows) with
+    the hidden activations in shared memory; falls back to one launch per layer for many rows or wide layers.
+    layers = [(w, b, post (scale, shift) | None, post_relu), ...]; a pending batch norm on x becomes the prologue and
+    an explicit `pre` affine is then folded into the first layer's weights (see _dense)."""
+    pre_relu = False
+    if isinstance(x, DeferredAffine):
+        if pre is not None:
+            w, b = _fold_into_weights(pre, layers[0][0], layers[0][1])
+            layers = [(w, b) + tuple(layers[0][2:])] + list(layers[1:])
+        pre, pre_relu, x = (x.scale, x.shift), x.relu, x.base
+    nd, h = _cnt(x), _hint(x)
+    rows = h if h else x.shape[0]
+    widths = [x.shape[1]] + [l[0].shape[1] for l in layers]
+    if rows <= 128 and max(widths) <= 1024 and len(layers) <= 4:
+        return _tag(ops.mlp_rows(x, layers, pre=pre, pre_relu=pre_relu, n_dev=nd), nd, h)
+    for i, (w, b, post, post_relu) in enumerate(layers):
+        x = _tag(ops.dense_layer(x, w, b, pre=pre if i == 0 else None, pre_relu=pre_relu if i == 0 else False,
+                                 post=post, post_relu=post_relu, n_dev=nd, rows_hint=h), nd, h)
+    return x
+
+
 _folded = {}
 
 
@@ -81,23 +103,23 @@ def batch_normalization(inputs, training, name, store=None):
 
 def MLP_2_hidden(features, numInputFeatures, hidden1_units, hidden2_units, numOutFeatures, layerName, keepProb,
                  isTraining, useDropOut=False, useInitBN=True, store=None):
-    """utils/MCNetworkUtils.py:20-69 (dropout is the identity at inference: keepProb = 1).  Three launches: the
-    initial batch norm is the prologue of layer 1, each hidden batch norm + ReLU the epilogue of its layer."""
+    """utils/MCNetworkUtils.py:20-69 (dropout is the identity at inference: keepProb = 1).  One launch for the
+    whole head: the initial batch norm is the prologue of layer 1, each hidden batch norm + ReLU the epilogue of
+    its layer."""
     vs = _store(store)
     pre = _bn_affine(numInputFeatures, isTraining, layerName + "_BN_Init", vs) if useInitBN else None
     w1 = vs.get_variable(layerName + '_weights1', [numInputFeatures, hidden1_units], "glorot")
     vs.add_to_collection('weight_decay_loss', w1)
     b1 = vs.get_variable(layerName + '_biases1', [hidden1_units], "zeros")
-    h1 = _dense(features, w1, b1, pre=pre, post=_bn_affine(hidden1_units, isTraining, layerName + "_BN_h1", vs),
-                post_relu=True)
+    post1 = _bn_affine(hidden1_units, isTraining, layerName + "_BN_h1", vs)
     w2 = vs.get_variable(layerName + '_weights2', [hidden1_units, hidden2_units], "glorot")
     vs.add_to_collection('weight_decay_loss', w2)
     b2 = vs.get_variable(layerName + '_biases2', [hidden2_units], "zeros")
-    h2 = _dense(h1, w2, b2, post=_bn_affine(hidden2_units, isTraining, layerName + "_BN_h2", vs), post_relu=True)
+    post2 = _bn_affine(hidden2_units, isTraining, layerName + "_BN_h2", vs)
     w3 = vs.get_variable(layerName + '_weights3', [hidden2_units, numOutFeatures], "glorot")
     vs.add_to_collection('weight_decay_loss', w3)
     b3 = vs.get_variable(layerName + '_biases3', [numOutFeatures], "zeros")
-    return _dense(h2, w3, b3)
+    return _mlp(features, [(w1, b1, post1, True), (w2, b2, post2, True), (w3, b3, None, False)], pre=pre)
 
 
 def MLP_1_hidden(features, numInputFeatures, hidden_units, numOutFeatures, layerName, keepProb, isTraining,
@@ -107,11 +129,11 @@ def MLP_1_hidden(features, numInputFeatures, hidden_units, numOutFeatures, layer
     w1 = vs.get_variable(layerName + '_weights1', [numInputFeatures, hidden_units], "glorot")
     vs.add_to_collection('weight_decay_loss', w1)
     b1 = vs.get_variable(layerName + '_biases1', [hidden_units], "zeros")
-    h = _dense(features, w1, b1, post=_bn_affine(hidden_units, isTraining, layerName + "_BN_h", vs), post_relu=True)
+    post = _bn_affine(hidden_units, isTraining, layerName + "_BN_h", vs)
     w2 = vs.get_variable(layerName + '_weights2', [hidden_units, numOutFeatures], "glorot")
     vs.add_to_collection('weight_decay_loss', w2)
     b2 = vs.get_variable(layerName + '_biases2', [numOutFeatures], "zeros")
-    return _dense(h, w2, b2)
+    return _mlp(features, [(w1, b1, post, True), (w2, b2, None, False)])
 
 
 def conv_1x1(layerName, inputs, numInputs, numOutFeatures, store=None):

@@ -55,6 +55,8 @@ SIGNATURES = {
     "mc_scale_shift_act": (_c_int, [_c_int, _ptr, _c_int, _ptr, _ptr, _ptr, _c_int, _ptr, _ptr]),
     "mc_dense_layer": (_c_int, [_c_int, _ptr, _c_int, _c_int, _c_int, _ptr, _ptr, _ptr, _c_int, _ptr, _ptr, _ptr, _ptr,
                                 _c_int, _ptr, _ptr]),
+    "mc_mlp_rows": (_c_int, [_c_int, _ptr, _c_int, _ptr, _ptr, _ptr, _ptr, _c_int, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr,
+                             _ptr]),
 }
 
 

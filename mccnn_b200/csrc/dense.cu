@@ -42,23 +42,11 @@ __device__ __forceinline__ float epilogue(float v, int c, const float* __restric
     return relu2 ? fmaxf(v, 0.0f) : v;
 }
 
-// one CTA per row; threads = (column c, K-slice s)
-__global__ void __launch_bounds__(kDnThreads)
-    dense_rows_kernel(const int* __restrict__ dRows, int capRows, int K, int N, const float* __restrict__ x,
-                      const float* __restrict__ s1, const float* __restrict__ t1, int relu1,
-                      const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ s2,
-                      const float* __restrict__ t2, int relu2, float* __restrict__ y) {
-    __shared__ float sA[kRowsMaxK];
-    __shared__ float sPart[kDnThreads];
-    const int rows = live_count(dRows, capRows);
-    const int r = blockIdx.x;
-    if (r >= rows) return;
-    for (int k = threadIdx.x; k < K; k += kDnThreads) {
-        float v = x[(size_t)r * K + k];
-        if (s1 != nullptr) v = fmaf(v, s1[k], t1[k]);
-        sA[k] = relu1 ? fmaxf(v, 0.0f) : v;
-    }
-    __syncthreads();
+// one layer of one row: out[c] = epilogue(sum_k sA[k] W[k][c]); threads = (column c, K-slice s); `out` may be shared
+// or global memory.  Ends with a barrier, so the caller may read `out` (shared) or overwrite sA right away.
+__device__ __forceinline__ void row_layer(const float* sA, float* sPart, int K, int N, const float* __restrict__ W,
+                                          const float* __restrict__ bias, const float* __restrict__ s2,
+                                          const float* __restrict__ t2, int relu2, float* out) {
     for (int c0 = 0; c0 < N; c0 += kDnThreads) {
         const int cols = min(N - c0, kDnThreads);
         const int slices = kDnThreads / cols;
@@ -87,9 +75,65 @@ __global__ void __launch_bounds__(kDnThreads)
         if (threadIdx.x < cols) {
             float v = 0.0f;
             for (int q = 0; q < slices; ++q) v += sPart[q * cols + threadIdx.x];  // fixed order: deterministic
-            y[(size_t)r * N + c0 + threadIdx.x] = epilogue(v, c0 + threadIdx.x, bias, s2, t2, relu2);
+            out[c0 + threadIdx.x] = epilogue(v, c0 + threadIdx.x, bias, s2, t2, relu2);
         }
         __syncthreads();
+    }
+}
+
+__device__ __forceinline__ void load_row(float* sA, int K, const float* __restrict__ x, const float* __restrict__ s1,
+                                         const float* __restrict__ t1, int relu1) {
+    for (int k = threadIdx.x; k < K; k += kDnThreads) {
+        float v = x[k];
+        if (s1 != nullptr) v = fmaf(v, s1[k], t1[k]);
+        sA[k] = relu1 ? fmaxf(v, 0.0f) : v;
+    }
+    __syncthreads();
+}
+
+// one CTA per row, one layer
+__global__ void __launch_bounds__(kDnThreads)
+    dense_rows_kernel(const int* __restrict__ dRows, int capRows, int K, int N, const float* __restrict__ x,
+                      const float* __restrict__ s1, const float* __restrict__ t1, int relu1,
+                      const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ s2,
+                      const float* __restrict__ t2, int relu2, float* __restrict__ y) {
+    __shared__ float sA[kRowsMaxK];
+    __shared__ float sPart[kDnThreads];
+    const int rows = live_count(dRows, capRows);
+    const int r = blockIdx.x;
+    if (r >= rows) return;
+    load_row(sA, K, x + (size_t)r * K, s1, t1, relu1);
+    row_layer(sA, sPart, K, N, W, bias, s2, t2, relu2, y + (size_t)r * N);
+}
+
+// one CTA per row, a whole MLP (the classification heads MLP_1_hidden / MLP_2_hidden): the hidden activations stay
+// in shared memory.  Same arithmetic, in the same order, as one dense_rows_kernel launch per layer.
+constexpr int kMlpMaxLayers = 4;
+struct MlpArgs {
+    int layers;
+    int dims[kMlpMaxLayers + 1];
+    const float* W[kMlpMaxLayers];
+    const float* bias[kMlpMaxLayers];
+    const float* scale[kMlpMaxLayers];
+    const float* shift[kMlpMaxLayers];
+    int relu[kMlpMaxLayers];
+};
+
+__global__ void __launch_bounds__(kDnThreads)
+    mlp_rows_kernel(const int* __restrict__ dRows, int capRows, const float* __restrict__ x,
+                    const float* __restrict__ s0, const float* __restrict__ t0, int relu0, const MlpArgs a,
+                    float* __restrict__ y) {
+    __shared__ float sBuf[2][kRowsMaxK];
+    __shared__ float sPart[kDnThreads];
+    const int rows = live_count(dRows, capRows);
+    const int r = blockIdx.x;
+    if (r >= rows) return;
+    load_row(sBuf[0], a.dims[0], x + (size_t)r * a.dims[0], s0, t0, relu0);
+    for (int l = 0; l < a.layers; ++l) {
+        const bool last = l == a.layers - 1;
+        float* out = last ? y + (size_t)r * a.dims[l + 1] : sBuf[(l + 1) & 1];
+        row_layer(sBuf[l & 1], sPart, a.dims[l], a.dims[l + 1], a.W[l], a.bias[l], a.scale[l], a.shift[l], a.relu[l],
+                  out);
     }
 }
 
@@ -202,4 +246,34 @@ extern "C" int mc_dense_layer(int numRows, const int* dNumRows, int numRowsHint,
                                                        y);
     }
     return check_launch("mc_dense_layer");
+}
+
+// A whole MLP on few rows in ONE launch (MLP_1_hidden / MLP_2_hidden, utils/MCNetworkUtils.py:20-107):
+//   a_0 = act0(x * s0 + t0);   a_{l+1} = act_l((a_l @ W[l] + bias[l]) * scale[l] + shift[l]);   y = a_numLayers
+// dims: numLayers + 1 host ints (input width, then every layer's output width, each <= 1024); W / bias / scale / shift:
+// host arrays of numLayers device pointers (bias, scale+shift may be NULL per layer); relu: numLayers host flags.
+extern "C" int mc_mlp_rows(int numRows, const int* dNumRows, int numLayers, const int* dims, const float* x,
+                           const float* s0, const float* t0, int relu0, const float* const* W,
+                           const float* const* bias, const float* const* scale, const float* const* shift,
+                           const int* relu, float* y, void* stream) {
+    MC_REQUIRE(numLayers >= 1 && numLayers <= kMlpMaxLayers, "mc_mlp_rows: between 1 and 4 layers");
+    MC_REQUIRE((s0 == nullptr) == (t0 == nullptr), "mc_mlp_rows: scale and shift come in pairs");
+    MlpArgs a;
+    a.layers = numLayers;
+    for (int l = 0; l <= numLayers; ++l) {
+        MC_REQUIRE(dims[l] > 0 && dims[l] <= kRowsMaxK, "mc_mlp_rows: layer widths must be in 1..1024");
+        a.dims[l] = dims[l];
+    }
+    for (int l = 0; l < numLayers; ++l) {
+        MC_REQUIRE(W[l] != nullptr, "mc_mlp_rows: weights required");
+        MC_REQUIRE((scale[l] == nullptr) == (shift[l] == nullptr), "mc_mlp_rows: scale and shift come in pairs");
+        a.W[l] = W[l];
+        a.bias[l] = bias[l];
+        a.scale[l] = scale[l];
+        a.shift[l] = shift[l];
+        a.relu[l] = relu[l];
+    }
+    if (numRows <= 0) return 0;
+    mlp_rows_kernel<<<numRows, kDnThreads, 0, (cudaStream_t)stream>>>(dNumRows, numRows, x, s0, t0, relu0, a, y);
+    return check_launch("mc_mlp_rows");
 }

@@ -379,7 +379,10 @@ __global__ void __launch_bounds__(kSelThreads)
             if (f) {
                 int pos = sh.phaseBase[f] + sh.running[f] + __popc(grp & ltMask);
                 for (int w = 0; w < warp; ++w) pos += sh.warpCnt[w][f];
-                tmpIdx[cLo + pos] = cLo + t;
+                if (cx.sAccIdx != nullptr)
+                    cx.sAccIdx[pos] = (unsigned short)t;  // the accepted lists are dead by now: reuse as the order
+                else
+                    tmpIdx[cLo + pos] = cLo + t;
             }
             __syncthreads();
             if (threadIdx.x >= 1 && threadIdx.x <= 27) {
@@ -403,15 +406,17 @@ __global__ void __launch_bounds__(kSelThreads)
     __syncthreads();
     const int base = sh.base;
     for (int t = threadIdx.x; t < mCloud; t += kSelThreads) {
-        const int i = tmpIdx[cLo + t];
+        const int i = cx.sAccIdx != nullptr ? cLo + cx.sAccIdx[t] : tmpIdx[cLo + t];
         const int pos = base + t;
         if (pos >= capOut) {
             if (dOverflow != nullptr) *dOverflow = 1;
             continue;
         }
-        outPts[(size_t)pos * 3] = pts[(size_t)i * 3];
-        outPts[(size_t)pos * 3 + 1] = pts[(size_t)i * 3 + 1];
-        outPts[(size_t)pos * 3 + 2] = pts[(size_t)i * 3 + 2];
+        float px, py, pz;
+        cx.point(i, px, py, pz);
+        outPts[(size_t)pos * 3] = px;
+        outPts[(size_t)pos * 3 + 1] = py;
+        outPts[(size_t)pos * 3 + 2] = pz;
         outBids[pos] = b;
         outIdx[pos] = i;
     }

@@ -272,3 +272,35 @@ def dense_layer(x, w, bias=None, pre=None, pre_relu=False, post=None, post_relu=
     check(lib.mc_dense_layer(x.shape[0], _p(n_dev), int(rows_hint or 0), K, N, _p(x), _p(s1), _p(t1), int(pre_relu), _p(w), _p(b), _p(s2),
                              _p(t2), int(post_relu), _p(y), _stream()))
     return y
+
+
+def mlp_rows(x, layers, pre=None, pre_relu=False, n_dev=None):
+    """A whole MLP on few rows in one launch: `layers` = [(w [K, N], bias | None, post (scale, shift) | None,
+    post_relu), ...]; a_0 = act(x * pre[0] + pre[1]).  Every width must be <= 1024."""
+    import ctypes
+    x = _f(x)
+    n = len(layers)
+    dims = [x.shape[1]] + [int(l[0].shape[1]) for l in layers]
+    keep = []
+
+    def ptr(t):
+        if t is None:
+            return None
+        t = _f(t)
+        keep.append(t)
+        return t.data_ptr()
+
+    W = (ctypes.c_void_p * n)(*[ptr(l[0]) for l in layers])
+    B = (ctypes.c_void_p * n)(*[ptr(l[1]) for l in layers])
+    S = (ctypes.c_void_p * n)(*[ptr(l[2][0]) if l[2] is not None else None for l in layers])
+    T = (ctypes.c_void_p * n)(*[ptr(l[2][1]) if l[2] is not None else None for l in layers])
+    R = (ctypes.c_int * n)(*[int(bool(l[3])) for l in layers])
+    D = (ctypes.c_int * (n + 1))(*dims)
+    for l, (k_in, layer) in enumerate(zip(dims[:-1], layers)):
+        if layer[0].shape[0] != k_in:
+            raise ValueError("mlp_rows: layer %d expects %d inputs, got %d" % (l, layer[0].shape[0], k_in))
+    y = torch.empty((x.shape[0], dims[-1]), dtype=_f32, device=_dev(x))
+    s0, t0 = (None, None) if pre is None else (_f(pre[0]), _f(pre[1]))
+    check(lib.mc_mlp_rows(x.shape[0], _p(n_dev), n, D, _p(x), _p(s0), _p(t0), int(bool(pre_relu)), W, B, S, T, R,
+                          _p(y), _stream()))
+    return y

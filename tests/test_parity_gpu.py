@@ -327,3 +327,42 @@ def test_deferred_batch_norm_is_folded_exactly(env):
     out = U.MLP_2_hidden(d, 64, 32, 16, 10, "head", 1.0, False, store=store)
     ref = U.MLP_2_hidden(d.materialize(), 64, 32, 16, 10, "head", 1.0, False, store=store)
     assert float((out - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
+
+
+def test_mlp_rows_equals_layer_by_layer(env):
+    """mc_mlp_rows (a whole classification head in one launch) does the same arithmetic in the same order as one
+    mc_dense_layer launch per layer: bit-identical, and 1e-5 relative against the float64 formulation."""
+    e = env
+    torch, T = e["torch"], e["T"]
+    from mccnn_b200 import ops
+    rng = np.random.default_rng(17)
+    for rows, dims in ((32, (256, 128, 64, 40)), (5, (7, 300, 3)), (64, (1024, 16)), (1, (3, 5, 7, 9, 11))):
+        x = T(rng.normal(size=(rows, dims[0])).astype(np.float32))
+        pre = (T(rng.uniform(0.5, 1.5, dims[0]).astype(np.float32)), T(rng.normal(size=dims[0]).astype(np.float32)))
+        layers = []
+        for k, n in zip(dims[:-1], dims[1:]):
+            w = T((rng.normal(size=(k, n)) / np.sqrt(k)).astype(np.float32))
+            b = T(rng.normal(size=n).astype(np.float32) * 0.1)
+            post = (T(rng.uniform(0.5, 1.5, n).astype(np.float32)), T(rng.normal(size=n).astype(np.float32) * 0.1))
+            layers.append((w, b, post, True))
+        layers[-1] = (layers[-1][0], None, None, False)
+        got = ops.mlp_rows(x, layers, pre=pre, pre_relu=True)
+        want = x
+        ref = torch.relu(x.double() * pre[0].double() + pre[1].double())
+        for i, (w, b, post, relu) in enumerate(layers):
+            want = ops.dense_layer(want, w, b, pre=pre if i == 0 else None, pre_relu=(i == 0), post=post,
+                                   post_relu=relu, rows_hint=1)
+            ref = ref @ w.double()
+            if b is not None:
+                ref = ref + b.double()
+            if post is not None:
+                ref = ref * post[0].double() + post[1].double()
+            if relu:
+                ref = torch.relu(ref)
+        assert torch.equal(got, want)
+        assert float((got.double() - ref).abs().max()) <= 2e-5 * float(ref.abs().max())
+    cnt = torch.tensor([3], dtype=torch.int32, device=e["dev"])
+    x = T(rng.normal(size=(8, 16)).astype(np.float32))
+    w = T(rng.normal(size=(16, 4)).astype(np.float32))
+    part = ops.mlp_rows(x, [(w, None, None, False)], n_dev=cnt)
+    assert torch.equal(part[:3], ops.mlp_rows(x, [(w, None, None, False)])[:3])
