@@ -540,8 +540,6 @@ def main():
     torch.cuda.set_device(dev)
 
     if args.impl == "reference":
-        if args.steps > 20:
-            args.steps = 20  # each reference step is ~100+ ms of launch-bound work
         line = run_reference(args, rank, world, dev)
         if line is not None:
             print(json.dumps(line))

@@ -12,7 +12,7 @@ import torch
 
 from . import ops
 from . import variables as _vars
-from .runtime import DeferredAffine, count_of as _cnt, hint_of as _hint, materialize as _real, tag as _tag
+from .runtime import DeferredAffine, count_of as _cnt, dispatch as _dispatch, hint_of as _hint, materialize as _real, tag as _tag
 
 BN_EPSILON = 1e-3  # tf.layers.batch_normalization default
 
@@ -94,6 +94,16 @@ def _affine_act(x, scale, shift, relu):
     """Inference batch norm (+ ReLU): returned as a pending per-column affine that the consumer folds into its own
     kernel (runtime.DeferredAffine); stacked on another pending one, the inner one is evaluated first."""
     return DeferredAffine(_real(x), scale, shift, relu)
+
+
+def concat(values, axis=1):
+    """tf.concat of feature matrices that live on the same point level (models/MCClass.py:69 and every encoder /
+    decoder skip link).  The one TensorFlow call of the model files that has to know about capacity-padded tensors:
+    the result keeps the live row count of its inputs and is issued on the stream of the current lane."""
+    vals = [_real(v) for v in values]
+    nd = next((c for c in (_cnt(v) for v in vals) if c is not None), None)
+    h = next((c for c in (_hint(v) for v in vals) if c is not None), None)
+    return _tag(_dispatch(vals, lambda: torch.cat(vals, axis)), nd, h)
 
 
 def batch_normalization(inputs, training, name, store=None):

@@ -1,2 +1,2 @@
 """Network topologies of the reference (models/*.py) expressed against mccnn_b200's builder API."""
-from . import MCClassS  # noqa: F401
+from . import MCClass, MCClassH, MCClassS, MCNorm, MCNormS, MCSeg, MCSegScanNet  # noqa: F401

@@ -84,3 +84,27 @@ def sum_err(a, b, scale):
     if a.size == 0:
         return 0.0
     return float((np.abs(a - b) / (s + 1e-30 + 1e-12 * s.max())).max())
+
+
+def named_variable(name, shape, seed=0):
+    """Deterministic value of the model variable `name` (float32 ndarray): weights Glorot-uniform with TensorFlow's
+    fan rule (variance_scaling factor 1, FAN_AVG, uniform -- utils/MCConvBuilder.py:394), everything that the reference
+    initialises to a constant (biases 0, gamma 1, beta 0, moving mean 0 / variance 1) is drawn non-trivially so that
+    every parameter path is exercised.  Seeded by the NAME, so the reference-model runner (oracle/ref_models.py) and the
+    GPU tests (tests/test_models_gpu.py) obtain identical parameters without storing them."""
+    import zlib
+    rng = np.random.default_rng([zlib.crc32(name.encode()), seed])
+    shape = tuple(int(s) for s in shape)
+    if name.endswith("/gamma") or name.endswith("/moving_variance"):
+        return rng.uniform(0.75, 1.25, shape).astype(np.float32)
+    if name.endswith("/beta") or name.endswith("/moving_mean") or "biases" in name:
+        return rng.uniform(-0.1, 0.1, shape).astype(np.float32)
+    if len(shape) == 1:
+        fi = fo = float(shape[0])
+    elif len(shape) == 2:
+        fi, fo = float(shape[0]), float(shape[1])
+    else:
+        rf = float(np.prod(shape[:-2]))
+        fi, fo = shape[-2] * rf, shape[-1] * rf
+    lim = math.sqrt(3.0 / ((fi + fo) / 2.0))
+    return rng.uniform(-lim, lim, shape).astype(np.float32)
