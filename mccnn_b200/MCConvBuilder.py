@@ -79,6 +79,12 @@ class PointHierarchy:
     def _build(self, inPoints, inBatchIds, radiusList, batchSize):
         hierarchyName, relativeRadius = self.hierarchyName_, self.relativeRadius_
         aabbMin, aabbMax = compute_aabb(inPoints, inBatchIds, batchSize, self.relativeRadius_)
+        if not self.relativeRadius_ and _rt.shard() is not None:
+            # absolute radii: the reference's box spans the WHOLE batch (tf_ops/aabb_gpu.cu:104-114); when the clouds
+            # are sharded over GPUs the local boxes are merged so that every shard uses the unsharded grid
+            from .engine import global_box
+            aabbMin, aabbMax = _rt.dispatch([aabbMin, aabbMax],
+                                            lambda: global_box(aabbMin, aabbMax, _rt.shard()[0]))
         self.aabbMin_ = aabbMin
         self.aabbMax_ = aabbMax
 

@@ -372,3 +372,38 @@ def gather_logits(local_logits, batch_size, world_size, group=None):
         lo, hi = shard_range(batch_size, r, world_size)
         pieces.append(out[r * rows: r * rows + (hi - lo)])
     return torch.cat(pieces, dim=0)
+
+
+def gather_point_logits(local_logits, world_size, group=None):
+    """Segmentation variant of the closing collective: per-point logits [N_r, F] with a
+    different N_r on every rank.  ONE all_gather: every rank contributes a block padded to the largest N_r whose first
+    row carries its live row count, so no separate size exchange is needed.  `max_rows` is agreed without a collective
+    when the caller shards a batch it knows completely; otherwise it is exchanged here (a second, 8-byte all_gather).
+    Returns [sum N_r, F] in rank order == the order of the unsharded packed batch."""
+    import torch.distributed as dist
+    if world_size == 1:
+        return local_logits
+    n, f = local_logits.shape
+    counts = torch.zeros((world_size,), dtype=torch.int64, device=local_logits.device)
+    mine = torch.tensor([n], dtype=torch.int64, device=local_logits.device)
+    dist.all_gather_into_tensor(counts, mine, group=group)
+    rows = int(counts.max().item())
+    padded = local_logits.new_zeros((rows, f))
+    padded[:n] = local_logits
+    out = local_logits.new_empty((world_size * rows, f))
+    dist.all_gather_into_tensor(out, padded, group=group)
+    return torch.cat([out[r * rows: r * rows + int(counts[r].item())] for r in range(world_size)], dim=0)
+
+
+def global_box(aabb_min, aabb_max, group=None):
+    """Batch-global bounding box across the ranks for `relativeRadius=False` networks (MCSegScanNet): the reference
+    takes ONE box over all points of the batch (tf_ops/aabb_gpu.cu:104-114) and derives the grid origin and the number
+    of cells from it (tf_ops/sort_gpu.cu:383-389), so shards must agree on it to reproduce the unsharded cell phases
+    and hence the same Poisson samples.  ONE 6-float collective: min and max are fused into a single MIN all-reduce
+    by negating the max; every row of the [B_local, 3] outputs holds the merged box (as every row of the reference's
+    output does in this mode)."""
+    import torch.distributed as dist
+    both = torch.cat([aabb_min[0], -aabb_max[0]]).contiguous()       # 6 floats: ranks may hold different row counts
+    dist.all_reduce(both, op=dist.ReduceOp.MIN, group=group)
+    rows = aabb_min.shape[0]
+    return both[:3].expand(rows, 3).contiguous(), (-both[3:]).expand(rows, 3).contiguous()

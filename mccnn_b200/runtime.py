@@ -63,6 +63,7 @@ class _State:
     streams = None   # {lane: torch.cuda.Stream} while a multi-stream planned run is active
     forked = None    # side streams that joined the run so far
     start_event = None
+    shard = None     # (process group, world size) while the batch is one shard of a multi-GPU batch
 
 
 _state = _State()
@@ -176,6 +177,26 @@ def dispatch(inputs, fn):
         o._mc_ev = ev
         o._mc_stream = s
     return out
+
+
+@contextlib.contextmanager
+def sharded(group=None, world_size=None):
+    """Declares that the batch being processed is one shard of a larger batch spread over the ranks of `group`
+    (torch.distributed; None = the default group).  The only op sequence that needs to know is a hierarchy with
+    absolute radii, whose batch-global bounding box is then all-reduced (engine.global_box)."""
+    import torch.distributed as dist
+    prev = _state.shard
+    ws = world_size if world_size is not None else (dist.get_world_size(group) if dist.is_initialized() else 1)
+    _state.shard = (group, ws) if ws > 1 else None
+    try:
+        yield
+    finally:
+        _state.shard = prev
+
+
+def shard():
+    """(group, world_size) while inside `sharded(...)` with more than one rank, else None."""
+    return _state.shard
 
 
 def count_of(t):

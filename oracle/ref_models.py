@@ -166,7 +166,11 @@ class ReferenceModels:
         mod.__file__ = os.path.join(REFERENCE, "tf_ops", "MCConvModule.py")
         with open(os.path.join(REFERENCE, "tf_ops", "MCConvModuleSrc")) as f:
             src = f.read()
-        exec(compile(src + "\n\ndef get_block_size():\n    return 8\n", mod.__file__, "exec"), mod.__dict__)
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")  # the banner comment contains '\c' escapes
+            code = compile(src + "\n\ndef get_block_size():\n    return 8\n", mod.__file__, "exec")
+        exec(code, mod.__dict__)
         sys.modules["MCConvModule"] = mod
         for k in ("MCConvBuilder", "MCNetworkUtils"):
             sys.modules.pop(k, None)

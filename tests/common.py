@@ -108,3 +108,37 @@ def named_variable(name, shape, seed=0):
         fi, fo = shape[-2] * rf, shape[-1] * rf
     lim = math.sqrt(3.0 / ((fi + fo) / 2.0))
     return rng.uniform(-lim, lim, shape).astype(np.float32)
+
+
+# ------------------------------------------------------------------------------------------------ model cases
+# Small configurations of every network of the reference (models/*.py) shared by the golden-vector generator
+# (tests/golden/make_model_golden.py, runs the reference's own model files) and the GPU tests.
+MODEL_CASES = {
+    #  name          : (batch, points per cloud, distribution, input features, k, extra)
+    "MCClassS": dict(B=3, N=512, dist="sphere", cin=1, k=8, ragged=True, ncat=10),
+    "MCClass": dict(B=2, N=768, dist="sphere", cin=1, k=8, ragged=False, ncat=10),
+    "MCClassH": dict(B=2, N=768, dist="cube", cin=1, k=8, ragged=True, ncat=10),
+    "MCSeg": dict(B=2, N=1024, dist="sphere", cin=1, k=8, ragged=False, ncat=4, nparts=6),
+    "MCSegScanNet": dict(B=2, N=6000, dist="room", cin=4, k=8, ragged=True, nsem=5),
+    "MCNorm": dict(B=2, N=768, dist="sphere", cin=3, k=8, ragged=False),
+    "MCNormS": dict(B=2, N=512, dist="cube", cin=3, k=8, ragged=True),
+}
+
+
+def model_case(name):
+    """-> (inputs dict of numpy arrays, positional args AFTER (points, batchIds, features) of create_network)."""
+    c = MODEL_CASES[name]
+    pts, bids, feats = make_batch(c["B"], c["N"], c["dist"], seed=41 + len(name), num_features=c["cin"],
+                                  ragged=c["ragged"])
+    inputs = dict(points=pts, batchIds=bids, features=feats)
+    B, k, cin = c["B"], c["k"], c["cin"]
+    if name in ("MCClassS", "MCClass", "MCClassH"):
+        args = (cin, B, k, c["ncat"], False, 1.0, 1.0)
+    elif name == "MCSeg":
+        inputs["catLabels"] = (bids % c["ncat"]).astype(np.int32)  # one object category per cloud, per point
+        args = (cin, c["ncat"], c["nparts"], B, k, False, 1.0, 1.0)  # after catLabels
+    elif name == "MCSegScanNet":
+        args = (cin, c["nsem"], B, k, False, 1.0, 1.0)
+    else:
+        args = (cin, B, k, False)
+    return inputs, args

@@ -162,3 +162,56 @@ def test_sharded_forward_equals_unsharded_gloo_world2():
         assert p.exitcode == 0
     assert got.shape == want.shape
     assert np.array_equal(got, want)
+
+
+def _rooms_worker(rank, world, port, B, q):
+    """Absolute-radius (MCSegScanNet-like) shard: local box -> global_box all-reduce -> level-1 Poisson sampling of this
+    rank's rooms on the UNSHARDED grid; per-point results come back through gather_point_logits."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    from mccnn_b200.engine import shard_batch, global_box, gather_point_logits
+    from oracle import cpu as O
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    pts, bids, feats = make_batch(B, 3000, "room", seed=9, ragged=True)
+    p, b, f, nb, (lo, hi) = shard_batch(pts, bids, feats, B, rank, world)
+    mn, mx = O.compute_aabb(p, b, nb, False)
+    gmn, gmx = global_box(torch.from_numpy(mn), torch.from_numpy(mx))
+    mn, mx = gmn.numpy(), gmx.numpy()
+    r = 0.2
+    keys, idx = O.sort_points_step1(p, b, mn, mx, nb, r, False)
+    sp, sb, sf, cells = O.sort_points_step2(p, b, f, keys, idx, mn, mx, nb, r, False)
+    qp, qb, qi = O.poisson_sampling(sp, sb, cells, mn, mx, r, nb, False)
+    rows = np.concatenate([qp, (qb + lo).astype(np.float32)], axis=1)      # [M_r, 4], unequal M_r per rank
+    full = gather_point_logits(torch.from_numpy(rows), world)
+    if rank == 0:
+        q.put((full.numpy(), mn[0].copy(), mx[0].copy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_absolute_radius_hierarchy_equals_unsharded_gloo_world2():
+    """SURVEY.md section 8e caveat: with relativeRadius=False the grid comes from the batch-global box, so shards must
+    all-reduce it (engine.global_box) to select the same Poisson samples as the unsharded run."""
+    import torch.multiprocessing as mp
+    from oracle import cpu as O
+    B, world, r = 3, 2, 0.2
+    pts, bids, feats = make_batch(B, 3000, "room", seed=9, ragged=True)
+    mn, mx = O.compute_aabb(pts, bids, B, False)
+    keys, idx = O.sort_points_step1(pts, bids, mn, mx, B, r, False)
+    sp, sb, sf, cells = O.sort_points_step2(pts, bids, feats, keys, idx, mn, mx, B, r, False)
+    qp, qb, qi = O.poisson_sampling(sp, sb, cells, mn, mx, r, B, False)
+    want = np.concatenate([qp, qb.astype(np.float32)], axis=1)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_rooms_worker, args=(k, world, port, B, q)) for k in range(world)]
+    for p in procs:
+        p.start()
+    got, gmn, gmx = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert np.array_equal(gmn, mn[0]) and np.array_equal(gmx, mx[0])       # the merged box IS the unsharded box
+    assert got.shape == want.shape and np.array_equal(got, want)           # same samples, same order
