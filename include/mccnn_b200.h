@@ -41,6 +41,11 @@ int mc_compute_aabb(int scaleInv, int numPoints, int batchSize, const float* pts
 int mc_determine_num_cells(int scaleInv, float cellSize, const float* aabbMin, const float* aabbMax, int* workspace,
                            int* hostOutNumCells, void* stream);
 
+/* Sync-free check used by planned / graph-captured forwards with absolute radii: ORs 1 into *dMismatchFlag when the
+ * box implies a number of cells (tf_ops/sort_gpu.cu:381-389) different from expectedNumCells. */
+int mc_verify_num_cells(float cellSize, const float* aabbMin, const float* aabbMax, int expectedNumCells,
+                        int* dMismatchFlag, void* stream);
+
 /* computeAuxiliarBuffersSize(int,int,int*,int*,int*) -- tf_ops/sort_gpu.cc:112-117, tf_ops/sort_gpu.cu:422-434 */
 long long mc_sort_step1_workspace_ints(int numPoints, int batchSize, int numCells);
 

@@ -72,8 +72,22 @@ def compute_aabb(inPts, inBatchIds, batchSize, scaleInv=True):
 
 
 def _num_cells(aabbMin, aabbMax, cellSize, scaleInv):
+    """determineNumCells (tf_ops/sort_gpu.cu:397-420).  Relative radii: host arithmetic.  Absolute radii: the count
+    depends on the batch's box -- one 4-byte D2H in exact mode (as the reference); recorded with the plan and merely
+    VERIFIED on the device in planned mode (a mismatch raises the plan's overflow flag, the engine re-records)."""
     _req(cellSize > 0.0, "expects a positive cell size")
-    return ops.num_cells(cellSize, scaleInv, aabbMin, aabbMax)
+    if scaleInv:
+        return ops.num_cells(cellSize, True, aabbMin, aabbMax)
+    mode = _rt.mode()
+    if mode == "planned":
+        plan = _rt.current_plan()
+        n = plan.next_flag()
+        ops.verify_num_cells(cellSize, aabbMin, aabbMax, n, plan.overflow)
+        return n
+    n = ops.num_cells(cellSize, False, aabbMin, aabbMax)
+    if mode == "record":
+        _rt.current_plan().flags.append(n)
+    return n
 
 
 @_scheduled

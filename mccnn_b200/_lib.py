@@ -25,6 +25,7 @@ SIGNATURES = {
     "mc_launch_count": (_c_ll, []),
     "mc_compute_aabb": (_c_int, [_c_int, _c_int, _c_int, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr]),
     "mc_determine_num_cells": (_c_int, [_c_int, _c_float, _ptr, _ptr, _ptr, _ptr, _ptr]),
+    "mc_verify_num_cells": (_c_int, [_c_float, _ptr, _ptr, _c_int, _ptr, _ptr]),
     "mc_sort_step1_workspace_ints": (_c_ll, [_c_int, _c_int, _c_int]),
     "mc_sort_points_step1": (_c_int, [_c_int, _ptr, _c_int, _c_int, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr]),
     "mc_sort_points_step2": (_c_int, [_c_int, _ptr, _c_int, _c_int, _c_int, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr,

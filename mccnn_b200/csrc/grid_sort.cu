@@ -187,10 +187,31 @@ __global__ void num_cells_kernel(float cellSize, const float* __restrict__ mn, c
     *out = n == 0 ? 1 : n;
 }
 
+// planned mode: the grid resolution was fixed when the plan was recorded; raise the flag if this batch's box asks for
+// a different one (the caller then re-records, exactly as for an exceeded capacity)
+__global__ void verify_num_cells_kernel(float cellSize, const float* __restrict__ mn, const float* __restrict__ mx,
+                                        int expected, int* __restrict__ flag) {
+    int n = (int)__fdiv_rn(max_extent(mn, mx, 0), cellSize);
+    if ((n == 0 ? 1 : n) != expected) atomicOr(flag, 1);
+}
+
 }  // namespace
 }  // namespace mc
 
 using namespace mc;
+
+// Sync-free companion of mc_determine_num_cells for absolute radii (scaleInv == 0): checks on the device that the
+// number of cells this batch's box implies (tf_ops/sort_gpu.cu:381-389) equals `expectedNumCells` and ORs 1 into
+// *dMismatchFlag otherwise.  Lets a captured forward reuse the grid resolution it was planned with.
+extern "C" int mc_verify_num_cells(float cellSize, const float* aabbMin, const float* aabbMax, int expectedNumCells,
+                                   int* dMismatchFlag, void* stream) {
+    MC_REQUIRE(cellSize > 0.0f, "mc_verify_num_cells: cell size must be positive");
+    MC_REQUIRE(dMismatchFlag != nullptr, "mc_verify_num_cells: flag required");
+    verify_num_cells_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(cellSize, aabbMin, aabbMax, expectedNumCells,
+                                                               dMismatchFlag);
+    count_launches(1);
+    return check_launch("mc_verify_num_cells");
+}
 
 // determineNumCells, tf_ops/sort_gpu.cu:397-420.  scale_inv: host arithmetic, no device work.  Otherwise the
 // count depends on row 0 of the box: one tiny kernel + one 4-byte D2H (the only sync; callers cache the result).

@@ -163,7 +163,7 @@ class PlannedForward:
             self._record(pts, bids, feats)
             s, f = self.plan.sizes, self.plan.flags
             sizes = list(s) if sizes is None else [max(a, b) for a, b in zip(sizes, s)]
-            flags = list(f) if flags is None else [a and b for a, b in zip(flags, f)]
+            flags = list(f) if flags is None else [(a and b) if isinstance(a, bool) else b for a, b in zip(flags, f)]
         self.plan.sizes, self.plan.flags = sizes, flags
         self.plan.finalize()
         self.graph = None

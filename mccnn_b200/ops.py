@@ -71,6 +71,11 @@ def num_cells(cell_size, scale_inv, aabb_min, aabb_max):
     return out.value
 
 
+def verify_num_cells(cell_size, aabb_min, aabb_max, expected, flag):
+    """Device-side check that the box still implies `expected` cells per axis (absolute radii); ORs 1 into `flag`."""
+    check(lib.mc_verify_num_cells(float(cell_size), _p(aabb_min), _p(aabb_max), int(expected), _p(flag), _stream()))
+
+
 def sort_points_step1(pts, bids, aabb_min, aabb_max, batch_size, n_cells, n_dev=None):
     pts, bids = _f(pts), _i(bids)
     dev = _dev(pts)

@@ -72,7 +72,11 @@ def test_model_matches_reference_model_file(name):
 
 
 @pytest.mark.parametrize("name", ["MCClassH", "MCSeg", "MCSegScanNet", "MCNorm"])
-def test_model_planned_and_graph_bit_identical(name):
+def test_model_planned_and_graph(name):
+    """Sync-free planned execution (capacity-padded tensors, device-resident counts) and its CUDA-graph replay.
+    Planned and replayed results are bit-identical to each other and across repetitions (every kernel is
+    deterministic).  Against the exact-mode run they agree to fp32 re-association only: spatial_conv picks its run
+    length per warp from the (capacity vs exact) sizes, which permutes the summation order."""
     import torch
     from mccnn_b200.engine import PlannedForward
     dev = torch.device("cuda:0")
@@ -81,9 +85,36 @@ def test_model_planned_and_graph_bit_identical(name):
     fn, store, t = _network(name, dev)
     x = (t["points"], t["batchIds"], t["features"])
     ref = fn(*x)[:rows].clone()
+    scale = float(ref.abs().max())
+    outs = []
     for use_graph in (False, True):
         eng = PlannedForward(fn, rows, use_graph=use_graph)
-        assert torch.equal(eng(*x), ref)                 # records (exact mode)
-        for _ in range(2):
-            assert torch.equal(eng(*x).clone(), ref)     # planned / replayed: no host sync, capacity-padded tensors
+        assert torch.equal(eng(*x), ref)                 # first call records: exact mode
+        a, b = eng(*x).clone(), eng(*x).clone()          # planned / replayed
+        assert torch.equal(a, b)
+        assert float((a - ref).abs().max()) <= 1e-5 * scale
         assert eng.stats["overflows"] == 0
+        outs.append(a)
+    assert torch.equal(outs[0], outs[1])                 # graph replay == eager planned
+    assert eng.stats["captures"] == 1
+
+
+def test_scannet_plan_detects_a_different_grid_resolution():
+    """Absolute radii: the number of cells comes from the batch's box.  A planned forward reuses the recorded value and
+    verifies it on the device (mc_verify_num_cells); a batch whose box implies another resolution must come back
+    flagged and be re-run exactly -- never computed on the wrong grid."""
+    import torch
+    from mccnn_b200.engine import PlannedForward
+    dev = torch.device("cuda:0")
+    fn, store, t = _network("MCSegScanNet", dev)
+    x = (t["points"], t["batchIds"], t["features"])
+    rows = x[0].shape[0]
+    eng = PlannedForward(fn, rows, use_graph=True)
+    eng(*x)
+    eng(*x)
+    assert eng.stats["overflows"] == 0
+    stretched = (x[0] * 1.5, x[1], x[2])                 # a larger room: more cells per axis for the same radii
+    want = fn(*stretched)[:rows].clone()
+    got = eng(*stretched)
+    assert eng.stats["overflows"] == 1
+    assert torch.equal(got, want)

@@ -36,6 +36,17 @@ def main():
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     for name in args.configs.split(","):
+        try:
+            run_config(name, args, dev)
+        except Exception as e:  # keep going: one failing configuration must not hide the others
+            import traceback
+            traceback.print_exc()
+            print({"config": name, "error": repr(e)[:300]}, flush=True)
+            torch.cuda.synchronize()
+
+
+def run_config(name, args, dev):
+    if True:
         c = dict(CONFIGS[name])
         c["N"] = int(c["N"] * args.scale)
         pts, bids, feats = make_batch(c["B"], c["N"], c["dist"], seed=3, num_features=c["cin"])
