@@ -238,6 +238,7 @@ class PipelinedForward:
                         for _ in range(depth)]
         self.streams = None
         self._events = [None] * depth
+        self._after = [None] * depth
         self._next = 0
 
     def calibrate(self, batches):
@@ -256,23 +257,30 @@ class PipelinedForward:
         torch.cuda.synchronize(dev)
         return plan
 
-    def _enqueue(self, run):
+    def _enqueue(self, run, after=None):
         lane = self._next
         self._next = (self._next + 1) % self.depth
         s = self.streams[lane]
         s.wait_stream(torch.cuda.current_stream())  # inputs produced on the caller's stream
         with torch.cuda.stream(s):
-            run(self.engines[lane])
+            out, flag = run(self.engines[lane])
+            # `after` runs ON THE LANE'S STREAM right behind the forward -- the place for the closing all_gather of a
+            # sharded batch: issued from the caller's stream it would chain every lane behind the previous one
+            self._after[lane] = after(out, flag) if after is not None else None
             ev = torch.cuda.Event()
             ev.record(s)
         self._events[lane] = ev
         return lane
 
-    def submit(self, pts, bids, feats):
-        return self._enqueue(lambda e: e.run_async(pts, bids, feats))
+    def submit(self, pts, bids, feats, after=None):
+        return self._enqueue(lambda e: e.run_async(pts, bids, feats), after)
 
-    def submit_packed(self, block):
-        return self._enqueue(lambda e: e.run_packed(block))
+    def submit_packed(self, block, after=None):
+        return self._enqueue(lambda e: e.run_packed(block), after)
+
+    def after_result(self, ticket):
+        """What the `after` callback of that submission returned (valid once result()/join() made it visible)."""
+        return self._after[ticket]
 
     def result(self, ticket, wait_on_host=False):
         ev = self._events[ticket]
@@ -298,10 +306,13 @@ class PipelinedHostForward:
         self.pipe = pipe
         self.device = torch.device(device)
         self._result_host = [None] * pipe.depth
+        self._extra_host = [None] * pipe.depth
         self._events = [None] * pipe.depth
         self._blocks = [None] * pipe.depth
 
-    def submit_packed(self, pinned_block):
+    def submit_packed(self, pinned_block, after=None):
+        """after(out) -> device tensor (e.g. engine.gather_logits over the ranks), evaluated on the lane's stream behind
+        the forward; result() then returns ITS host copy instead of the local logits."""
         lane = self.pipe._next
         if self._blocks[lane] is not None:
             raise RuntimeError("PipelinedHostForward: %d results outstanding -- call result() on the oldest ticket "
@@ -313,6 +324,13 @@ class PipelinedHostForward:
         with torch.cuda.stream(s):
             eng.run_packed(pinned_block)                                   # one H2D + one graph launch
             self._result_host[lane].copy_(eng._result, non_blocking=True)  # one D2H: logits + overflow flag
+            if after is not None:
+                extra = after(eng._out_view)
+                if self._extra_host[lane] is None or self._extra_host[lane].shape != extra.shape:
+                    self._extra_host[lane] = torch.empty(extra.shape, dtype=extra.dtype).pin_memory()
+                self._extra_host[lane].copy_(extra, non_blocking=True)
+                extra.record_stream(s)
+            self._has_extra = after is not None
             ev = torch.cuda.Event()
             ev.record(s)
         self._events[lane], self._blocks[lane] = ev, pinned_block
@@ -334,6 +352,8 @@ class PipelinedHostForward:
                 eng.run_async(*(v.clone() for v in eng._static_in))  # re-capture for the following steps
             self.pipe.streams[ticket].synchronize()
             return out.cpu()
+        if getattr(self, "_has_extra", False):
+            return self._extra_host[ticket]
         return host[: rows * cols].view(rows, cols)
 
 
@@ -362,6 +382,11 @@ def gather_logits(local_logits, batch_size, world_size, group=None):
     import torch.distributed as dist
     if world_size == 1:
         return local_logits
+    if batch_size % world_size == 0 and local_logits.shape[0] * world_size == batch_size:
+        # equal shards (the benchmark's case): the collective alone, no padding / re-assembly kernels
+        out = local_logits.new_empty((batch_size, local_logits.shape[1]))
+        dist.all_gather_into_tensor(out, local_logits.contiguous(), group=group)
+        return out
     rows = (batch_size + world_size - 1) // world_size
     padded = local_logits.new_zeros((rows, local_logits.shape[1]))
     padded[: local_logits.shape[0]] = local_logits

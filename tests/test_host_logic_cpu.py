@@ -141,12 +141,13 @@ def _params(k, numCat=10, seed=0):
     return p
 
 
-def test_sharded_forward_equals_unsharded_gloo_world2():
+@pytest.mark.parametrize("B", [5, 4])  # unequal shards (padded gather) and equal shards (bare all_gather)
+def test_sharded_forward_equals_unsharded_gloo_world2(B):
     """Clouds are independent units: computing each rank's clouds separately and all_gathering
     the logits reproduces the single-process result exactly.  Runs the real collective on the gloo backend."""
     import torch.multiprocessing as mp
     from oracle import pipeline as OP
-    B, k, world = 5, 8, 2
+    k, world = 8, 2
     pts, bids, feats = make_batch(B, 256, "sphere", seed=5)
     want, trace = OP.mcclasss_forward(pts, bids, feats, 1, B, k, 10, _params(k))
     assert want.shape == (B, 10) and trace[0]["levels"][-1] == B
