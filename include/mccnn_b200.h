@@ -147,6 +147,33 @@ int mc_spatial_conv(int avg, int scaleInv, int numNeighbors, const int* dNumNeig
                     const float* aabbMax, const float* W1, const float* b1, const float* W2, const float* b2,
                     const float* Wout, const float* bout, float* workspace, float* outFeatures, void* stream);
 
+/* ---- backward ops: the gradient launchers of the reference's op library ---------------- */
+
+long long mc_spatial_conv_grad_workspace_floats(int numNeighbors, int numInFeatures, int numOutFeatures, int combin);
+
+/* spatialConvGradsCPU -- tf_ops/spatial_conv.cc:130-156, tf_ops/spatial_conv.cu:873-966.
+ * Inputs as mc_spatial_conv plus outFeatureGrads [numSamples, outC]; outputs: featureGrads [numPoints, numInFeatures]
+ * and one gradient buffer per parameter in that parameter's flat layout ([3*8nb], [8nb], [8nb*8], [8nb], [8nb*8],
+ * [8nb]); all fully written.  Exact extents only (training is not graph-captured). */
+int mc_spatial_conv_grad(int avg, int scaleInv, int numNeighbors, int numInFeatures, int numOutFeatures,
+                         int numSamples, int numPoints, int combin, float radius, int batchSize, const float* pts,
+                         const int* batchIds, const float* features, const float* pdfs, const float* samples,
+                         const int* startIdx, const int* pairs, const float* aabbMin, const float* aabbMax,
+                         const float* W1, const float* b1, const float* W2, const float* b2, const float* Wout,
+                         const float* bout, const float* outFeatureGrads, float* workspace, float* featureGrads,
+                         float* W1Grads, float* b1Grads, float* W2Grads, float* b2Grads, float* WoutGrads,
+                         float* boutGrads, void* stream);
+
+/* sortPointsStep2GradGPUKernel -- tf_ops/sort_gpu.cc:147-154, tf_ops/sort_gpu.cu:499-513:
+ * inPtsGrads[i,:] = outPtsGrads[newIdx[i],:], inFeatureGrads[i,:] = outFeatureGrads[newIdx[i],:] */
+int mc_sort_points_step2_grad(int numPoints, int numFeatures, const float* outPtsGrads, const float* outFeatureGrads,
+                              const int* newIdx, float* inPtsGrads, float* inFeatureGrads, void* stream);
+
+/* getFeaturesSampledPointsGradients -- tf_ops/poisson_sampling.cc:102-107, tf_ops/poisson_sampling.cu:260-274:
+ * featureGrads = 0; featureGrads[idx[s],:] = outFeatureGrads[s,:] */
+int mc_get_sampled_features_grad(int numPoints, int numFeatures, int numSamples, const int* idx,
+                                 const float* outFeatureGrads, float* featureGrads, void* stream);
+
 /* Dense glue between the convolutions (TensorFlow ops in the reference: utils/MCNetworkUtils.py:20-142).
  * mc_scale_shift_act: y = act(x * scale + shift) -- inference batch norm (+ ReLU), statistics folded by the caller.
  * mc_dense_layer:     y = act2((act1(x * s1 + t1) @ W + bias) * s2 + t2), W [K, N] row-major; s1/t1, bias, s2/t2 may

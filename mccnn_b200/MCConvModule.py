@@ -313,3 +313,175 @@ def spatial_conv(inPts, inFeatures, inBatchIds, inPDFs, inSamplePts, neighStartI
                            biases2, weightsOut, biasesOut, numOutFeatures, combin, radius, scaleInv, avg, md,
                            _cnt(packedNeighs))
     return _tag(out, md, _rt.hint_of(inSamplePts))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Backward ops.  The raw gradient ops carry the names and argument orders of the reference's
+# op library (MCConv_module.sort_points_step2_grad / get_sampled_features_grad / spatial_conv_grad as called from
+# tf_ops/MCConvModuleSrc:30-32,62-64,74-81); the gradient WIRING that MCConvModuleSrc registers with TensorFlow
+# (@tf.RegisterGradient, :28-45,60-81) is expressed as torch.autograd Functions: the five differentiable wrappers
+# (sort_points_step2, sort_features, sort_features_back, get_sampled_features, spatial_conv) take that route whenever
+# an input requires grad.  Exact mode only -- training runs are not plan-captured.
+
+def sort_points_step2_grad(indexs, outPtsGrad, outFeaturesGrad):
+    """SortPointsStep2Grad, tf_ops/sort_gpu.cc:380-437 -> (inPtsGrad [N,3], inFeatureGrad [N,C])."""
+    _req(indexs.dim() == 1, "SortPointsStep2GradOp expects indexs of shape (numPoints)")
+    N = indexs.shape[0]
+    _req(outPtsGrad.dim() == 2 and tuple(outPtsGrad.shape) == (N, 3),
+         "SortPointsStep2GradOp expects point gradients of shape (numPoints, 3)")
+    _req(outFeaturesGrad.dim() == 2 and outFeaturesGrad.shape[0] == N,
+         "SortPointsStep2GradOp expects feature gradients of shape (numPoints, C)")
+    return ops.sort_points_step2_grad(indexs, outPtsGrad, outFeaturesGrad)
+
+
+def get_sampled_features_grad(inSampledIndexs, pInFeatures, inOutFeatureGrad):
+    """GetSampledFeaturesGrad, tf_ops/poisson_sampling.cc:57-66,252-300 -> featureGrads [N, C]."""
+    _req(inSampledIndexs.dim() == 1, "GetSampledFeaturesGradOp expects indexs of shape (numSamples)")
+    _req(pInFeatures.dim() == 2, "GetSampledFeaturesGradOp expects features of shape (numPoints, C)")
+    _req(inOutFeatureGrad.dim() == 2 and
+         tuple(inOutFeatureGrad.shape) == (inSampledIndexs.shape[0], pInFeatures.shape[1]),
+         "GetSampledFeaturesGradOp expects gradients of shape (numSamples, C)")
+    return ops.get_sampled_features_grad(inSampledIndexs, pInFeatures, inOutFeatureGrad)
+
+
+def spatial_conv_grad(inPts, inFeatures, inBatchIds, inPDFs, inSamplePts, neighStartIndexs, packedNeighs, aabbMin,
+                      aabbMax, weights1, biases1, weights2, biases2, weightsOut, biasesOut, inOutFeatureGrads,
+                      numOutFeatures, combin, batchSize, radius, scaleInv, avg):
+    """SpatialConvGrad, tf_ops/spatial_conv.cc:56-96,323-470 (the OP's input order: W1, b1, W2, b2, Wout, bout) ->
+    (featureGrads [N,C], weights1Grads, biases1Grads, weights2Grads, biases2Grads, weightsOutGrads, biasesOutGrads),
+    every parameter gradient shaped like (and laid out as) its parameter."""
+    _req(numOutFeatures > 0, "SpatialConvGradOp expects a positive number of output features")
+    _req(radius > 0.0, "SpatialConvGradOp expects a positive radius")
+    _req(batchSize > 0, "SpatialConvGradOp expects a positive batch size")
+    _req(inPts.dim() == 2 and inPts.shape[1] == 3, "SpatialConvGradOp expects points with three components")
+    N, C = inPts.shape[0], inFeatures.shape[1]
+    _req(inFeatures.dim() == 2 and inFeatures.shape[0] == N, "SpatialConvGradOp expects features of shape (numPoints, C)")
+    M, K = inSamplePts.shape[0], packedNeighs.shape[0]
+    outC = numOutFeatures if combin else C
+    _req(inOutFeatureGrads.dim() == 2 and tuple(inOutFeatureGrads.shape) == (M, outC),
+         "SpatialConvGradOp expects output gradients of shape (numSamples, numOutFeatures)")
+    _req(inPDFs.shape[0] == K and neighStartIndexs.shape[0] == M, "SpatialConvGradOp expects a consistent neighbor list")
+    bs = ops.get_block_size()
+    nOut = C * numOutFeatures if combin else C
+    _req(weights1.dim() == 2 and weights1.shape[0] == 3 and weights1.shape[1] % bs == 0 and
+         weights1.shape[1] >= (nOut + bs - 1) // bs * bs, "SpatialConvGradOp expects a correct first hidden layer")
+    _req(tuple(weights2.shape) == (bs, weights1.shape[1]), "SpatialConvGradOp expects a correct second hidden layer")
+    _req(tuple(weightsOut.shape) == (bs, weights1.shape[1]), "SpatialConvGradOp expects a correct output layer")
+    if not combin:
+        _req(weightsOut.shape[1] == C and numOutFeatures == C,
+             "SpatialConvGradOp expects the same number of features in the input and the output")
+    return ops.spatial_conv_grad(inPts, inFeatures, inBatchIds.reshape(-1), inPDFs.reshape(-1), inSamplePts,
+                                 neighStartIndexs.reshape(-1), packedNeighs, aabbMin, aabbMax, weights1, biases1,
+                                 weights2, biases2, weightsOut, biasesOut, inOutFeatureGrads, numOutFeatures, combin,
+                                 radius, scaleInv, avg)
+
+
+def _wants_grad(*tensors):
+    return torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors)
+
+
+def _exact_only(name):
+    if _rt.mode() == "planned":
+        raise RuntimeError("mccnn_b200: %s cannot be differentiated inside a planned (capacity-padded) run" % name)
+
+
+_fwd = {"sort_points_step2": sort_points_step2, "sort_features": sort_features,
+        "sort_features_back": sort_features_back, "get_sampled_features": get_sampled_features,
+        "spatial_conv": spatial_conv}
+
+
+class _SortPointsStep2(torch.autograd.Function):  # MCConvModuleSrc:28-32
+    @staticmethod
+    def forward(ctx, inPts, inFeatures, rest):
+        ctx.save_for_backward(rest[2])  # indexs
+        p, b, f, cells = _fwd["sort_points_step2"](inPts, rest[0], inFeatures, *rest[1:])
+        ctx.mark_non_differentiable(b, cells)
+        return p, b, f, cells
+
+    @staticmethod
+    def backward(ctx, gp, gb, gf, gc):
+        (indexs,) = ctx.saved_tensors
+        gp = torch.zeros((indexs.shape[0], 3), device=indexs.device) if gp is None else gp
+        ip, iF = sort_points_step2_grad(indexs, gp.contiguous(), gf.contiguous())
+        return ip, iF, None
+
+
+class _SortFeatures(torch.autograd.Function):  # MCConvModuleSrc:33-37: grad = sort_features_back(grads, indexs)
+    @staticmethod
+    def forward(ctx, inFeatures, indexs):
+        ctx.save_for_backward(indexs)
+        return _fwd["sort_features"](inFeatures, indexs)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _fwd["sort_features_back"](g.contiguous(), ctx.saved_tensors[0]), None
+
+
+class _SortFeaturesBack(torch.autograd.Function):  # MCConvModuleSrc:39-43: grad = sort_features_back_grad(idx, g)
+    @staticmethod
+    def forward(ctx, inFeatures, indexs):
+        ctx.save_for_backward(indexs)
+        return _fwd["sort_features_back"](inFeatures, indexs)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _fwd["sort_features"](g.contiguous(), ctx.saved_tensors[0]), None
+
+
+class _GetSampledFeatures(torch.autograd.Function):  # MCConvModuleSrc:60-64
+    @staticmethod
+    def forward(ctx, inSampledIndexs, pInFeatures):
+        ctx.save_for_backward(inSampledIndexs, pInFeatures)
+        return _fwd["get_sampled_features"](inSampledIndexs, pInFeatures)
+
+    @staticmethod
+    def backward(ctx, g):
+        idx, feats = ctx.saved_tensors
+        return None, get_sampled_features_grad(idx, feats, g.contiguous())
+
+
+class _SpatialConv(torch.autograd.Function):  # MCConvModuleSrc:74-81
+    @staticmethod
+    def forward(ctx, inFeatures, weights1, weights2, weightsOut, biases1, biases2, biasesOut, geo, attrs):
+        inPts, inBatchIds, inPDFs, inSamplePts, start, pairs, aabbMin, aabbMax = geo
+        ctx.save_for_backward(inFeatures, weights1, weights2, weightsOut, biases1, biases2, biasesOut, *geo)
+        ctx.attrs = attrs
+        return _fwd["spatial_conv"](inPts, inFeatures, inBatchIds, inPDFs, inSamplePts, start, pairs, aabbMin, aabbMax,
+                                    weights1, weights2, weightsOut, biases1, biases2, biasesOut, *attrs)
+
+    @staticmethod
+    def backward(ctx, g):
+        feats, w1, w2, wo, b1, b2, bo, pts, bids, pdfs, samples, start, pairs, mn, mx = ctx.saved_tensors
+        dF, dW1, db1, dW2, db2, dWo, dbo = spatial_conv_grad(
+            pts, feats, bids, pdfs, samples, start, pairs, mn, mx, w1, b1, w2, b2, wo, bo, g.contiguous(), *ctx.attrs)
+        return dF, dW1, dW2, dWo, db1, db2, dbo, None, None
+
+
+def _differentiable(name, picks, route):
+    plain = _fwd[name]
+
+    import functools
+
+    @functools.wraps(plain)
+    def wrapper(*args, **kwargs):
+        if kwargs or not _wants_grad(*[args[i] for i in picks if i < len(args)]):
+            return plain(*args, **kwargs)
+        _exact_only(name)
+        args = tuple(_rt.materialize(a) for a in args)
+        return route(*args)
+    return wrapper
+
+
+sort_points_step2 = _differentiable(
+    "sort_points_step2", (0, 2),
+    lambda inPts, inBatchIds, inFeatures, *rest: _SortPointsStep2.apply(inPts, inFeatures, (inBatchIds,) + rest))
+sort_features = _differentiable("sort_features", (0,), lambda f, idx: _SortFeatures.apply(f, idx))
+sort_features_back = _differentiable("sort_features_back", (0,), lambda f, idx: _SortFeaturesBack.apply(f, idx))
+get_sampled_features = _differentiable("get_sampled_features", (1,), lambda idx, f: _GetSampledFeatures.apply(idx, f))
+spatial_conv = _differentiable(
+    "spatial_conv", (1, 9, 10, 11, 12, 13, 14),
+    lambda inPts, inFeatures, inBatchIds, inPDFs, inSamplePts, start, pairs, mn, mx, w1, w2, wo, b1, b2, bo, *attrs:
+    _SpatialConv.apply(inFeatures, w1, w2, wo, b1, b2, bo,
+                       (inPts, inBatchIds, inPDFs, inSamplePts, start, pairs, mn, mx), attrs))
+
+__all__ += ["sort_points_step2_grad", "get_sampled_features_grad", "spatial_conv_grad"]

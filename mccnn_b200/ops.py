@@ -255,6 +255,42 @@ def spatial_conv(pts, feats, bids, pdfs, samples, start, pairs, aabb_min, aabb_m
     return out
 
 
+def spatial_conv_grad(pts, feats, bids, pdfs, samples, start, pairs, aabb_min, aabb_max, w1, b1, w2, b2, wout, bout,
+                      out_grad, num_out_features, combin, radius, scale_inv, avg):
+    """-> (featureGrads [N, C], dW1, db1, dW2, db2, dWout, dbout), each shaped like its parameter."""
+    pts, feats, bids, pdfs, samples = _f(pts), _f(feats), _i(bids), _f(pdfs), _f(samples)
+    start, pairs, out_grad = _i(start), _i(pairs), _f(out_grad)
+    w1, b1, w2, b2, wout, bout = (_f(t) for t in (w1, b1, w2, b2, wout, bout))
+    dev = _dev(pts)
+    M, K, C, N = samples.shape[0], pairs.shape[0], feats.shape[1], pts.shape[0]
+    d_feat = torch.empty((N, C), dtype=_f32, device=dev)
+    grads = [torch.empty_like(t) for t in (w1, b1, w2, b2, wout, bout)]
+    ws = torch.empty((lib.mc_spatial_conv_grad_workspace_floats(K, C, num_out_features, int(combin)),), dtype=_f32,
+                     device=dev)
+    check(lib.mc_spatial_conv_grad(int(avg), int(scale_inv), K, C, num_out_features, M, N, int(combin), float(radius),
+                                   aabb_min.shape[0], _p(pts), _p(bids), _p(feats), _p(pdfs), _p(samples), _p(start),
+                                   _p(pairs), _p(aabb_min), _p(aabb_max), _p(w1), _p(b1), _p(w2), _p(b2), _p(wout),
+                                   _p(bout), _p(out_grad), _p(ws), _p(d_feat), _p(grads[0]), _p(grads[1]),
+                                   _p(grads[2]), _p(grads[3]), _p(grads[4]), _p(grads[5]), _stream()))
+    return (d_feat,) + tuple(grads)
+
+
+def sort_points_step2_grad(new_idx, out_pts_grad, out_feat_grad):
+    new_idx, gp, gf = _i(new_idx), _f(out_pts_grad), _f(out_feat_grad)
+    ip, i_f = torch.empty_like(gp), torch.empty_like(gf)
+    check(lib.mc_sort_points_step2_grad(new_idx.shape[0], gf.shape[1], _p(gp), _p(gf), _p(new_idx), _p(ip), _p(i_f),
+                                        _stream()))
+    return ip, i_f
+
+
+def get_sampled_features_grad(idx, feats, out_grad):
+    idx, feats, out_grad = _i(idx), _f(feats), _f(out_grad)
+    g = torch.empty_like(feats)
+    check(lib.mc_get_sampled_features_grad(feats.shape[0], feats.shape[1], idx.shape[0], _p(idx), _p(out_grad), _p(g),
+                                           _stream()))
+    return g
+
+
 def scale_shift_act(x, scale, shift, relu, n_dev=None):
     """y = act(x * scale + shift) per column (inference batch norm + ReLU), live rows only."""
     x, scale, shift = _f(x), _f(scale), _f(shift)

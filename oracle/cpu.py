@@ -164,3 +164,41 @@ def spatial_conv(inPts, inFeatures, inBatchIds, inPDFs, inSamplePts, neighStartI
                            _p(start), _p(pairs), _p(mn), _p(mx), _p(w1), _p(b1), _p(w2), _p(b2), _p(wo), _p(bo),
                            _ci(2 if abs_sum else int(accum_double)), _p(out))
     return out
+
+
+def spatial_conv_grad(inPts, inFeatures, inBatchIds, inPDFs, inSamplePts, neighStartIndexs, packedNeighs, aabbMin,
+                      aabbMax, weights1, biases1, weights2, biases2, weightsOut, biasesOut, inOutFeatureGrads,
+                      numOutFeatures, combin, batchSize, radius, scaleInv, avg, abs_sum=False):
+    """SpatialConvGrad in the OP's input order (tf_ops/spatial_conv.cc:56-96: W1, b1, W2, b2, Wout, bout, then the
+    incoming gradient) -> (featureGrads [N,C], weights1Grads, biases1Grads, weights2Grads, biases2Grads,
+    weightsOutGrads, biasesOutGrads), each shaped like its parameter.  Accumulated in float64, rounded once."""
+    pts, feats, bids = _f(inPts), _f(inFeatures), _i(inBatchIds).reshape(-1)
+    pdfs, samples = _f(inPDFs).reshape(-1), _f(inSamplePts)
+    start, pairs, mn, mx = _i(neighStartIndexs).reshape(-1), _i(packedNeighs), _f(aabbMin), _f(aabbMax)
+    w1, b1, w2, b2, wo, bo = (_f(a) for a in (weights1, biases1, weights2, biases2, weightsOut, biasesOut))
+    og = _f(inOutFeatureGrads)
+    M, K, C, N = samples.shape[0], pairs.shape[0], feats.shape[1], pts.shape[0]
+    dF = np.empty((N, C), np.float32)
+    outs = [np.empty_like(a) for a in (w1, b1, w2, b2, wo, bo)]
+    lib().orc_spatial_conv_grad(_ci(int(avg)), _ci(int(scaleInv)), _ci(K), _ci(C), _ci(numOutFeatures), _ci(M), _ci(N),
+                                _ci(int(combin)), _cf(radius), _p(pts), _p(bids), _p(feats), _p(pdfs), _p(samples),
+                                _p(start), _p(pairs), _p(mn), _p(mx), _p(w1), _p(b1), _p(w2), _p(b2), _p(wo), _p(bo),
+                                _p(og), _ci(int(abs_sum)), _p(dF), _p(outs[0]), _p(outs[1]), _p(outs[2]), _p(outs[3]),
+                                _p(outs[4]), _p(outs[5]))
+    return (dF,) + tuple(outs)
+
+
+def sort_points_step2_grad(indexs, outPtsGrad, outFeaturesGrad):
+    """SortPointsStep2Grad (tf_ops/sort_gpu.cc:380-437) -> (inPtsGrad, inFeatureGrad)."""
+    idx, gp, gf = _i(indexs), _f(outPtsGrad), _f(outFeaturesGrad)
+    ip, iF = np.empty_like(gp), np.empty_like(gf)
+    lib().orc_sort_step2_grad(_ci(idx.shape[0]), _ci(gf.shape[1]), _p(idx), _p(gp), _p(gf), _p(ip), _p(iF))
+    return ip, iF
+
+
+def get_sampled_features_grad(inSampledIndexs, pInFeatures, inOutFeatureGrad):
+    """GetSampledFeaturesGrad (tf_ops/poisson_sampling.cc:252-300) -> featureGrads [N, C]."""
+    idx, f, g = _i(inSampledIndexs), _f(pInFeatures), _f(inOutFeatureGrad)
+    out = np.empty_like(f)
+    lib().orc_get_sampled_features_grad(_ci(idx.shape[0]), _ci(f.shape[1]), _ci(f.shape[0]), _p(idx), _p(g), _p(out))
+    return out

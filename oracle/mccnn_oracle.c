@@ -380,4 +380,130 @@ void orc_spatial_conv(int avg, int scaleInv, int K, int C, int Co, int M, int co
     free(accf);
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * spatial_conv_grad  (tf_ops/spatial_conv.cu:327-460 computedconvj_d, :563-700 computedconvj_dNoCombin,
+ *                     host spatialConvGradsCPU :873-966)
+ *   for pair p = (j, i), block q, forward recomputed: z1 = W1 d + b1, z2 = W2 relu(z1) + b2 (:362-378);
+ *   neuron n = 8q + t < nOut: c = n % C, o = combin ? n / C : c, f = feat[j,c], g = outGrad[i,o], w = pdf * cnt
+ *     common = (f * g) / w                       dWo[n,u] += common * relu(z2[u]);  dbo[n] += common   (:386-397)
+ *     dFeat[j,c] += g * (Wo[n] . relu(z2) + bo[n]) / w                                                  (:399-401)
+ *   dz2[t] = (z2[t] >= 0) * (sum_{n in block, n < nOut} g_n f_n Wo[n,t]) / w                          (:404-416)
+ *     dW2[t,u] += dz2[t] * relu(z1[u]);  db2[t] += dz2[t]                                               (:421-427)
+ *   dz1[t] = (z1[t] >= 0) * sum_i dz2[i] W2[i,t]                                                        (:430-437)
+ *     dW1[t,a] += dz1[t] * d[a];  db1[t] += dz1[t]                                                      (:442-447)
+ *   Note the ReLU derivative is taken with >= (1 at exactly 0).  The reference accumulates with float atomicAdd in
+ *   arbitrary order; here: double accumulators, rounded once (accumDouble) or float accumulation in pair order.
+ *   All gradient buffers are zero-filled first; the reference leaves the padding neurons (>= nOut) of the output
+ *   layer's gradient untouched (:905-906) -- canonical value 0.
+ *   absSum != 0: instead of the gradients, the sums of |contributions| (the error scale of each float sum).
+ * ---------------------------------------------------------------------------------------------- */
+void orc_spatial_conv_grad(int avg, int scaleInv, int K, int C, int Co, int M, int N, int combin, float radius,
+                           const float *pts, const int *bids, const float *feats, const float *pdfs,
+                           const float *samples, const int *start, const int *pairs, const float *mn, const float *mx,
+                           const float *W1, const float *b1, const float *W2, const float *b2, const float *Wo,
+                           const float *bo, const float *outGrad, int absSum, float *dFeat, float *dW1, float *db1,
+                           float *dW2, float *db2, float *dWo, float *dbo) {
+    int nOut = combin ? Co * C : C;
+    int outC = combin ? Co : C;
+    int nb = nOut / ORC_BLOCK_MLP + ((nOut % ORC_BLOCK_MLP) ? 1 : 0);
+    int nn = nb * ORC_BLOCK_MLP;
+    size_t nF = (size_t)(N > 0 ? N : 1) * C;
+    double *aF = (double *)calloc(nF, sizeof(double));
+    double *aW1 = (double *)calloc((size_t)nn * 3, sizeof(double)), *ab1 = (double *)calloc(nn, sizeof(double));
+    double *aW2 = (double *)calloc((size_t)nn * 8, sizeof(double)), *ab2 = (double *)calloc(nn, sizeof(double));
+    double *aWo = (double *)calloc((size_t)nn * 8, sizeof(double)), *abo = (double *)calloc(nn, sizeof(double));
+#define ORC_ACC(dst, v) ((dst) += absSum ? fabs((double)(v)) : (double)(v))
+    for (int p = 0; p < K; ++p) {
+        int j = pairs[p * 2], i = pairs[p * 2 + 1];
+        int b = bids[j];
+        float r = scaled_radius(scaleInv, radius, max_extent(mn, mx, b));
+        float d[3] = {(pts[j * 3] - samples[i * 3]) / r, (pts[j * 3 + 1] - samples[i * 3 + 1]) / r,
+                      (pts[j * 3 + 2] - samples[i * 3 + 2]) / r};
+        int lo = start[i];
+        int hi = (i < M - 1) ? start[i + 1] : K;
+        float cnt = avg ? (float)(hi - lo) : 1.0f;
+        float w = pdfs[p] * cnt;
+        for (int q = 0; q < nb; ++q) {
+            float z1[ORC_BLOCK_MLP], z2[ORC_BLOCK_MLP], dz2[ORC_BLOCK_MLP], dz1[ORC_BLOCK_MLP];
+            for (int t = 0; t < ORC_BLOCK_MLP; ++t) {
+                int nr = q * ORC_BLOCK_MLP + t;
+                z1[t] = d[0] * W1[nr * 3] + d[1] * W1[nr * 3 + 1] + d[2] * W1[nr * 3 + 2] + b1[nr];
+            }
+            for (int t = 0; t < ORC_BLOCK_MLP; ++t) {
+                int nr = q * ORC_BLOCK_MLP + t;
+                float a = 0.0f;
+                for (int u = 0; u < ORC_BLOCK_MLP; ++u) a += (z1[u] > 0.0f ? z1[u] : 0.0f) * W2[nr * ORC_BLOCK_MLP + u];
+                z2[t] = a + b2[nr];
+            }
+            for (int t = 0; t < ORC_BLOCK_MLP; ++t) {
+                int nr = q * ORC_BLOCK_MLP + t;
+                if (nr >= nOut) continue;
+                int c = nr % C, o = combin ? nr / C : c;
+                float f = feats[(size_t)j * C + c], g = outGrad[(size_t)i * outC + o];
+                float common = (f * g) / w;
+                float a = 0.0f;
+                for (int u = 0; u < ORC_BLOCK_MLP; ++u) {
+                    float h2 = z2[u] > 0.0f ? z2[u] : 0.0f;
+                    ORC_ACC(aWo[(size_t)nr * 8 + u], common * h2);
+                    a += h2 * Wo[nr * ORC_BLOCK_MLP + u];
+                }
+                ORC_ACC(abo[nr], common);
+                a += bo[nr];
+                ORC_ACC(aF[(size_t)j * C + c], g * a / w);
+            }
+            int numOuts = nOut - q * ORC_BLOCK_MLP;
+            if (numOuts > ORC_BLOCK_MLP) numOuts = ORC_BLOCK_MLP;
+            for (int t = 0; t < ORC_BLOCK_MLP; ++t) {
+                float a = 0.0f;
+                for (int k = 0; k < numOuts; ++k) {
+                    int nr = q * ORC_BLOCK_MLP + k;
+                    int c = nr % C, o = combin ? nr / C : c;
+                    a += outGrad[(size_t)i * outC + o] * feats[(size_t)j * C + c] * Wo[nr * ORC_BLOCK_MLP + t];
+                }
+                dz2[t] = ((z2[t] >= 0.0f ? 1.0f : 0.0f) * a) / w;
+            }
+            for (int t = 0; t < ORC_BLOCK_MLP; ++t) {
+                int nr = q * ORC_BLOCK_MLP + t;
+                for (int u = 0; u < ORC_BLOCK_MLP; ++u)
+                    ORC_ACC(aW2[(size_t)nr * 8 + u], dz2[t] * (z1[u] > 0.0f ? z1[u] : 0.0f));
+                ORC_ACC(ab2[nr], dz2[t]);
+            }
+            for (int t = 0; t < ORC_BLOCK_MLP; ++t) {
+                float a = 0.0f;
+                for (int k = 0; k < ORC_BLOCK_MLP; ++k) a += dz2[k] * W2[(q * ORC_BLOCK_MLP + k) * ORC_BLOCK_MLP + t];
+                dz1[t] = (z1[t] >= 0.0f ? 1.0f : 0.0f) * a;
+            }
+            for (int t = 0; t < ORC_BLOCK_MLP; ++t) {
+                int nr = q * ORC_BLOCK_MLP + t;
+                for (int a3 = 0; a3 < 3; ++a3) ORC_ACC(aW1[(size_t)nr * 3 + a3], dz1[t] * d[a3]);
+                ORC_ACC(ab1[nr], dz1[t]);
+            }
+        }
+    }
+#undef ORC_ACC
+    for (size_t e = 0; e < (size_t)N * C; ++e) dFeat[e] = (float)aF[e];
+    for (int e = 0; e < nn * 3; ++e) dW1[e] = (float)aW1[e];
+    for (int e = 0; e < nn * 8; ++e) dW2[e] = (float)aW2[e], dWo[e] = (float)aWo[e];
+    for (int e = 0; e < nn; ++e) db1[e] = (float)ab1[e], db2[e] = (float)ab2[e], dbo[e] = (float)abo[e];
+    free(aF), free(aW1), free(ab1), free(aW2), free(ab2), free(aWo), free(abo);
+}
+
+/* sortPointsStep2GradGPUKernel (tf_ops/sort_gpu.cu:260-277,499-513): in*Grad[i] = out*Grad[newIdx[i]] */
+void orc_sort_step2_grad(int N, int C, const int *newIdx, const float *outPtsGrad, const float *outFeatGrad,
+                         float *inPtsGrad, float *inFeatGrad) {
+    for (int i = 0; i < N; ++i) {
+        int s = newIdx[i];
+        for (int a = 0; a < 3; ++a) inPtsGrad[(size_t)i * 3 + a] = outPtsGrad[(size_t)s * 3 + a];
+        for (int c = 0; c < C; ++c) inFeatGrad[(size_t)i * C + c] = outFeatGrad[(size_t)s * C + c];
+    }
+}
+
+/* getFeaturesSampledPointsGradients (tf_ops/poisson_sampling.cu:158-171,260-274): zeros, then
+ * featGrad[idx[s],:] = outGrad[s,:] */
+void orc_get_sampled_features_grad(int M, int C, int N, const int *idx, const float *outGrad, float *featGrad) {
+    memset(featGrad, 0, sizeof(float) * (size_t)N * C);
+    for (int s = 0; s < M; ++s)
+        for (int c = 0; c < C; ++c) featGrad[(size_t)idx[s] * C + c] = outGrad[(size_t)s * C + c];
+}
+
 int orc_block_size(void) { return ORC_BLOCK_MLP; }

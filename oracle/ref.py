@@ -160,3 +160,36 @@ def spatial_conv(inPts, inFeatures, inBatchIds, inPDFs, inSamplePts, neighStartI
                            _p(start), _p(pairs), _p(aabbMin), _p(aabbMax), _p(w1), _p(b1), _p(w2), _p(b2), _p(wo),
                            _p(bo), _p(out))
     return out
+
+
+def spatial_conv_grad(inPts, inFeatures, inBatchIds, inPDFs, inSamplePts, neighStartIndexs, packedNeighs, aabbMin,
+                      aabbMax, weights1, biases1, weights2, biases2, weightsOut, biasesOut, inOutFeatureGrads,
+                      numOutFeatures, combin, batchSize, radius, scaleInv, avg):
+    """SpatialConvGrad through the reference's spatialConvGradsCPU; op input order (spatial_conv.cc:56-96)."""
+    pts, feats, bids, pdfs, samples = _f(inPts), _f(inFeatures), _i(inBatchIds), _f(inPDFs), _f(inSamplePts)
+    start, pairs = _i(neighStartIndexs), _i(packedNeighs)
+    w1, b1, w2, b2, wo, bo = (_f(t) for t in (weights1, biases1, weights2, biases2, weightsOut, biasesOut))
+    og = _f(inOutFeatureGrads)
+    M, K, C, N = samples.shape[0], pairs.shape[0], feats.shape[1], pts.shape[0]
+    dF = torch.zeros((N, C), dtype=_f32, device=pts.device)
+    g = [torch.zeros_like(t) for t in (w1, b1, w2, b2, wo, bo)]
+    lib().ref_spatial_conv_grad(_ci(int(avg)), _ci(int(scaleInv)), _ci(K), _ci(C), _ci(numOutFeatures), _ci(M),
+                                _ci(N), _ci(int(combin)), _cf(radius), _p(pts), _p(bids), _p(feats), _p(pdfs),
+                                _p(samples), _p(start), _p(pairs), _p(aabbMin), _p(aabbMax), _p(w1), _p(b1), _p(w2),
+                                _p(b2), _p(wo), _p(bo), _p(og), _p(dF), _p(g[0]), _p(g[1]), _p(g[2]), _p(g[3]),
+                                _p(g[4]), _p(g[5]))
+    return (dF,) + tuple(g)
+
+
+def sort_points_step2_grad(indexs, outPtsGrad, outFeaturesGrad):
+    idx, gp, gf = _i(indexs), _f(outPtsGrad), _f(outFeaturesGrad)
+    ip, iF = torch.empty_like(gp), torch.empty_like(gf)
+    lib().ref_sort_points_step2_grad(_ci(idx.shape[0]), _ci(gf.shape[1]), _p(gp), _p(gf), _p(idx), _p(ip), _p(iF))
+    return ip, iF
+
+
+def get_sampled_features_grad(inSampledIndexs, pInFeatures, inOutFeatureGrad):
+    idx, f, g = _i(inSampledIndexs), _f(pInFeatures), _f(inOutFeatureGrad)
+    out = torch.empty_like(f)
+    lib().ref_get_sampled_features_grad(_ci(f.shape[0]), _ci(f.shape[1]), _ci(idx.shape[0]), _p(idx), _p(g), _p(out))
+    return out

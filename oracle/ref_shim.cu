@@ -67,6 +67,22 @@ void spatialConvCPU(bool pAvg, bool pScaleInv, int pNumNeighbors, int pNumInFeat
                     const float* pBiases1, const float* pWeights2, const float* pBiases2, const float* pWeightsOut,
                     const float* pBiasesOut, float* pOutFeatues);
 
+void spatialConvGradsCPU(bool pAvg, bool pScaleInv, int pNumNeighbors, int pNumInFeatures, int pNumOutFeatures,
+                         int pNumSamples, int pNumPoints, bool pCombin, float pRadius, const float* pInPoints,
+                         const int* pBatchIds, const float* pInFeatures, const float* pPDFs, const float* pSamples,
+                         const int* pStartIndexs, const int* pPackedNeighs, const float* pAABBMin,
+                         const float* pAABBMax, const float* pWeights1, const float* pBiases1,
+                         const float* pWeights2, const float* pBiases2, const float* pWeightsOut,
+                         const float* pBiasesOut, const float* pInOutFeatueGrads, float* pOutFeatureGrads,
+                         float* pWeights1Grads, float* pWeight2Grads, float* pWeightOutGrads, float* pBiases1Grads,
+                         float* pBiases2Grads, float* pBiasesOutGrads);
+void sortPointsStep2GradGPUKernel(const int pNumPoints, const int pNumFeatures, const float* pOutGradients,
+                                  const float* pOutFeatureGradients, const int* pNewIndexs, float* pInGradients,
+                                  float* pInFeatureGradients);
+void getFeaturesSampledPointsGradients(int pNumPoints, int pNumFeatures, int pNumSampledPoints,
+                                       const int* pInPointsIndexs, const float* pInOutFeatureGrad,
+                                       float* pOutInFeaturesGradients);
+
 namespace {
 // grow-only temp pool standing in for TF's allocate_temp
 struct Slot {
@@ -193,6 +209,30 @@ void ref_spatial_conv(int avg, int scaleInv, int K, int C, int Co, int M, int co
                       const float* bo, float* out) {
     spatialConvCPU(avg != 0, scaleInv != 0, K, C, Co, M, combin != 0, radius, pts, bids, feats, pdfs, samples,
                    start, pairs, mn, mx, W1, b1, W2, b2, Wo, bo, out);
+}
+
+// SpatialConvGradOp::Compute, spatial_conv.cc:323-470: gradient buffers shaped like the parameters; the caller
+// zero-fills them first because the reference only clears the first numNeurons*8 entries of the output layer's
+// gradient (spatial_conv.cu:905-906) and TensorFlow hands it uninitialised memory for the rest
+void ref_spatial_conv_grad(int avg, int scaleInv, int K, int C, int Co, int M, int N, int combin, float radius,
+                           const float* pts, const int* bids, const float* feats, const float* pdfs,
+                           const float* samples, const int* start, const int* pairs, const float* mn,
+                           const float* mx, const float* W1, const float* b1, const float* W2, const float* b2,
+                           const float* Wo, const float* bo, const float* outGrad, float* dFeat, float* dW1,
+                           float* db1, float* dW2, float* db2, float* dWo, float* dbo) {
+    spatialConvGradsCPU(avg != 0, scaleInv != 0, K, C, Co, M, N, combin != 0, radius, pts, bids, feats, pdfs, samples,
+                        start, pairs, mn, mx, W1, b1, W2, b2, Wo, bo, outGrad, dFeat, dW1, dW2, dWo, db1, db2, dbo);
+}
+
+// SortPointsStep2GradOp::Compute, sort_gpu.cc:380-437
+void ref_sort_points_step2_grad(int N, int C, const float* outPtsGrad, const float* outFeatGrad, const int* newIdx,
+                                float* inPtsGrad, float* inFeatGrad) {
+    sortPointsStep2GradGPUKernel(N, C, outPtsGrad, outFeatGrad, newIdx, inPtsGrad, inFeatGrad);
+}
+
+// GetSampledFeaturesGradOp::Compute, poisson_sampling.cc:252-300
+void ref_get_sampled_features_grad(int N, int C, int M, const int* idx, const float* outGrad, float* featGrad) {
+    getFeaturesSampledPointsGradients(N, C, M, idx, outGrad, featGrad);
 }
 
 int ref_sync(void) { return (int)cudaDeviceSynchronize(); }
