@@ -227,13 +227,28 @@ def run_ours(args, rank, world, dev):
     for i in range(n_batches, n_pipe):
         pipe_res.append(pack_batch(*(torch.from_numpy(a).to(dev)
                                      for a in make_batch(B, P, "sphere", seed=1000 * rank + i))))
-    pipe = PipelinedForward(fn, B, depth=depth, slack=1.3)
-    pipe.calibrate(resident)
+    # multi-GPU: the step's single collective (all_gather of the per-cloud logits) is captured INTO each lane's CUDA
+    # graph (one NCCL communicator per lane: lanes run concurrently), so a step stays one graph launch on the host.
+    # Fallback if the capture is refused: the collective is issued on the lane's stream right behind the replay.
+    gather_mode, after = "none", None
+    pipe = None
+    if world > 1:
+        try:
+            groups = [dist.new_group(list(range(world))) for _ in range(depth)]
+            pipe = PipelinedForward(fn, B, depth=depth, slack=1.3, epilogues=[
+                (lambda o, g=g: gather_logits(o, B * world, world, group=g)) for g in groups])
+            pipe.calibrate(resident)
+            gather_mode = "all_gather captured in each lane's CUDA graph (one NCCL communicator per lane)"
+        except Exception as exc:  # noqa: BLE001
+            sys.stderr.write("bench: graph-captured all_gather unavailable (%r); issuing it per step\n" % (exc,))
+            pipe = None
+    if pipe is None:
+        pipe = PipelinedForward(fn, B, depth=depth, slack=1.3)
+        pipe.calibrate(resident)
+        if world > 1:
+            gather_mode = "all_gather issued on the lane's stream behind each graph replay"
+            after = lambda out, flag: gather_logits(out, B * world, world)  # noqa: E731
     pflags = torch.zeros((1,), dtype=torch.int32, device=dev)
-
-    # multi-GPU: the step's single collective (all_gather of the per-cloud logits) is issued on the lane's own stream
-    # right behind its forward, so the lanes stay independent
-    after = (lambda out, flag: gather_logits(out, B * world, world)) if world > 1 else None
 
     def pstep(i):
         return pipe.submit_packed(pipe_res[i % n_pipe], after=after)
@@ -383,7 +398,7 @@ def run_ours(args, rank, world, dev):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
-    after_h = (lambda out: gather_logits(out, B * world, world)) if world > 1 else None  # host gets ALL logits
+    after_h = (lambda out: gather_logits(out, B * world, world)) if after is not None else None  # host gets ALL logits
     t0 = time.perf_counter()
     tickets = []
     for i in range(args.steps):
@@ -403,7 +418,7 @@ def run_ours(args, rank, world, dev):
     e2e_s = float(t.item())
     h2d, d2h = hf.bytes_per_call(*pinned[0], B, NUM_CAT)
     if world > 1:  # whole job: every rank copies its batch in and its result block + the gathered logits out
-        h2d, d2h = h2d * world, (d2h + B * world * NUM_CAT * 4) * world
+        h2d, d2h = h2d * world, (B * world * NUM_CAT * 4 + 4 + (d2h if after is not None else 0)) * world
     clocks = sampler.stop()  # sampled across the value, per-op and e2e regions
 
     line = None
@@ -417,6 +432,7 @@ def run_ours(args, rank, world, dev):
             "config": {"workload": "MCClassS forward (models/MCClassS.py), %d clouds x %d points per GPU, k=%d, "
                                    "%d classes, 1 input feature" % (B, P, k, NUM_CAT),
                        "parallelism": "dp%d (clouds sharded, one all_gather of logits)" % world,
+                       "collective": gather_mode,
                        "concurrency": "%d forwards in flight per GPU (independent CUDA graphs on %d streams); every "
                                       "step is a complete forward of its own batch" % (depth, depth),
                        "l2": "timed region rotates over %d distinct resident batches (%.0f MB of inputs > 126 MB L2); "

@@ -55,10 +55,14 @@ def pack_batch(pts, bids, feats, pin=False):
 
 
 class PlannedForward:
-    def __init__(self, fn, out_rows, use_graph=True, slack=1.3, multistream=True):
+    def __init__(self, fn, out_rows, use_graph=True, slack=1.3, multistream=True, epilogue=None):
         """fn(points, batchIds, features) -> [>= out_rows, F] tensor; out_rows rows of it are the result.
-        multistream: overlap the hierarchy / convolution-geometry / feature chains on three streams (runtime.planned)."""
+        multistream: overlap the hierarchy / convolution-geometry / feature chains on three streams (runtime.planned).
+        epilogue(result) -> tensor: applied to the out_rows result rows in every mode and CAPTURED INTO THE GRAPH with
+        the forward -- the place for the closing all_gather of a sharded batch (NCCL collectives are capturable), so
+        that a multi-GPU step still costs one graph launch on the host."""
         self.fn = fn
+        self.epilogue = epilogue
         self.multistream = multistream
         self.out_rows = out_rows
         self.use_graph = use_graph
@@ -81,7 +85,11 @@ class PlannedForward:
         self.graph = None
         self._shape_key = (tuple(pts.shape), tuple(feats.shape))
         self.stats["records"] += 1
-        return out[: self.out_rows]
+        return self._finish(out)
+
+    def _finish(self, out):
+        res = out[: self.out_rows]
+        return self.epilogue(res) if self.epilogue is not None else res
 
     def _planned(self, pts, bids, feats):
         with _rt.planned(self.plan, pts.device, multistream=self.multistream):
@@ -96,18 +104,18 @@ class PlannedForward:
         self.plan.begin(pts.device)
         side = torch.cuda.Stream(device=pts.device)
         side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):  # warm-up outside capture (allocator, lazy module loading)
-            self._planned(*self._static_in)
+        with torch.cuda.stream(side):  # warm-up outside capture (allocator, lazy module loading, NCCL communicator)
+            self._finish(self._planned(*self._static_in))
         torch.cuda.current_stream().wait_stream(side)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             self.plan.overflow.zero_()
-            out = self._planned(*self._static_in)
-            rows, cols = self.out_rows, out.shape[1]
+            out = self._finish(self._planned(*self._static_in))
+            rows, cols = out.shape
             self._result = torch.empty((rows * cols + 1,), dtype=torch.float32, device=pts.device)
             self._out_view = self._result[: rows * cols].view(rows, cols)
             self._flag_view = self._result[rows * cols:].view(torch.int32)
-            self._out_view.copy_(out[:rows])
+            self._out_view.copy_(out)
             self._flag_view.copy_(self.plan.overflow)
         self.graph = g
         self.stats["captures"] += 1
@@ -133,7 +141,7 @@ class PlannedForward:
         if not self.use_graph:
             self.plan.overflow.zero_()
             out = self._planned(pts, bids, feats)
-            return out[: self.out_rows], self.plan.overflow
+            return self._finish(out), self.plan.overflow
         for v, t in zip(self._static_in, (pts, bids, feats)):
             v.copy_(t, non_blocking=True)
         self.graph.replay()
@@ -153,8 +161,14 @@ class PlannedForward:
         out, flag = self.run_async(pts, bids, feats)
         if int(flag.item()) != 0:
             self.stats["overflows"] += 1
+            self._no_solo_repair()
             out = self._record(pts, bids, feats)
         return out
+
+    def _no_solo_repair(self):
+        if self.epilogue is not None:
+            raise RuntimeError("mccnn_b200: a planned capacity was exceeded on a step whose graph contains a "
+                               "collective; one rank cannot re-run it alone -- re-calibrate with a larger slack")
 
     def calibrate(self, batches):
         """Record several representative batches (same shapes) and plan for the element-wise maximum of their sizes."""
@@ -232,10 +246,13 @@ class PipelinedForward:
     result(ticket) makes the caller's stream (or the host) wait for that forward only and returns
     (out, overflow_flag) device tensors, valid until the lane is reused."""
 
-    def __init__(self, fn, out_rows, depth=4, slack=1.3, multistream=True):
+    def __init__(self, fn, out_rows, depth=4, slack=1.3, multistream=True, epilogues=None):
+        """epilogues: one callable per lane (see PlannedForward).  Lanes run concurrently, so collectives in them must
+        use ONE PROCESS GROUP PER LANE: an NCCL communicator may not be driven from two streams at once."""
         self.depth = depth
-        self.engines = [PlannedForward(fn, out_rows, use_graph=True, slack=slack, multistream=multistream)
-                        for _ in range(depth)]
+        self.engines = [PlannedForward(fn, out_rows, use_graph=True, slack=slack, multistream=multistream,
+                                       epilogue=None if epilogues is None else epilogues[i])
+                        for i in range(depth)]
         self.streams = None
         self._events = [None] * depth
         self._after = [None] * depth
@@ -347,6 +364,7 @@ class PipelinedHostForward:
         host = self._result_host[ticket]
         if int(host[rows * cols:].view(torch.int32)[0]) != 0:  # planned capacity exceeded: exact re-run of this batch
             eng.stats["overflows"] += 1
+            eng._no_solo_repair()
             with torch.cuda.stream(self.pipe.streams[ticket]):
                 out = eng._record(*(v.clone() for v in eng._static_in))
                 eng.run_async(*(v.clone() for v in eng._static_in))  # re-capture for the following steps
