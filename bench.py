@@ -232,20 +232,39 @@ def run_ours(args, rank, world, dev):
     # Fallback if the capture is refused: the collective is issued on the lane's stream right behind the replay.
     gather_mode, after = "none", None
     pipe = None
-    if world > 1:
-        try:
-            groups = [dist.new_group(list(range(world))) for _ in range(depth)]
-            pipe = PipelinedForward(fn, B, depth=depth, slack=1.3, epilogues=[
-                (lambda o, g=g: gather_logits(o, B * world, world, group=g)) for g in groups])
-            pipe.calibrate(resident)
-            gather_mode = "all_gather captured in each lane's CUDA graph (one NCCL communicator per lane)"
-        except Exception as exc:  # noqa: BLE001
-            sys.stderr.write("bench: graph-captured all_gather unavailable (%r); issuing it per step\n" % (exc,))
-            pipe = None
+    if world > 1 and os.environ.get("MCCNN_BENCH_DIAG_NO_GATHER") == "1":
+        gather_mode = "DIAGNOSTIC: collective skipped in the pipelined loops (not a valid bench line)"
+        pipe = PipelinedForward(fn, B, depth=depth, slack=1.3)
+        pipe.calibrate(resident)
+    elif world > 1:
+        # (1) own kernel over NVLink peer memory (csrc/peer_gather.cu), captured into each lane's graph;
+        # (2) NCCL all_gather captured into each lane's graph (one communicator per lane); (3) NCCL per step
+        want = os.environ.get("MCCNN_GATHER", "peer")
+        if want == "peer":
+            try:
+                from mccnn_b200.engine import PeerGather
+                gathers = [PeerGather(B, NUM_CAT, dev) for _ in range(depth)]
+                pipe = PipelinedForward(fn, B, depth=depth, slack=1.3, epilogues=gathers)
+                pipe.calibrate(resident)
+                gather_mode = ("all_gather as ONE own kernel over NVLink peer memory (symmetric buffers, peer stores + "
+                               "flags; csrc/peer_gather.cu), a node of each lane's CUDA graph")
+            except Exception as exc:  # noqa: BLE001
+                sys.stderr.write("bench: peer-memory all_gather unavailable (%r); trying NCCL in the graph\n" % (exc,))
+                pipe = None
+        if pipe is None and want in ("peer", "nccl_graph"):
+            try:
+                groups = [dist.new_group(list(range(world))) for _ in range(depth)]
+                pipe = PipelinedForward(fn, B, depth=depth, slack=1.3, epilogues=[
+                    (lambda o, g=g: gather_logits(o, B * world, world, group=g)) for g in groups])
+                pipe.calibrate(resident)
+                gather_mode = "NCCL all_gather captured in each lane's CUDA graph (one communicator per lane)"
+            except Exception as exc:  # noqa: BLE001
+                sys.stderr.write("bench: graph-captured all_gather unavailable (%r); issuing it per step\n" % (exc,))
+                pipe = None
     if pipe is None:
         pipe = PipelinedForward(fn, B, depth=depth, slack=1.3)
         pipe.calibrate(resident)
-        if world > 1:
+        if world > 1 and not gather_mode.startswith("DIAG"):
             gather_mode = "all_gather issued on the lane's stream behind each graph replay"
             after = lambda out, flag: gather_logits(out, B * world, world)  # noqa: E731
     pflags = torch.zeros((1,), dtype=torch.int32, device=dev)
@@ -449,8 +468,8 @@ def run_ours(args, rank, world, dev):
                                       "ms_per_step": round(e2e_latency_s * 1e3, 5)},
                     "note": "%d host calls in flight; each copies its batch from pinned host memory, runs the forward "
                             "and returns logits + overflow flag to the host, every result is read on the host" % depth},
-            "gpu_launches": launches_per_forward * args.steps,
-            "gpu_launches_per_step": launches_per_forward,
+            "gpu_launches": (launches_per_forward + int("peer memory" in gather_mode)) * args.steps,
+            "gpu_launches_per_step": launches_per_forward + int("peer memory" in gather_mode),
             "wall_s_timed_region": round(t_wall_pipe, 4),
             "plan_overflows": overflowed,
             "roofline": roofline,
@@ -579,8 +598,17 @@ def main():
     ap.add_argument("--pipeline", type=int, default=4, help="forwards in flight for the throughput numbers")
     args = ap.parse_args()
 
+    # stdout carries exactly ONE line, the JSON: everything else any library prints there (e.g. NCCL's version banner)
+    # is sent to stderr
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = sys.stderr
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # the step's collective moves ~5 KB per rank: one NCCL channel (one CTA) is plenty, and every extra channel is an
+    # SM that spins while the lane waits for its peer
+    os.environ.setdefault("NCCL_MAX_NCHANNELS", os.environ.get("MCCNN_NCCL_CHANNELS", "1"))
+    os.environ.setdefault("NCCL_MIN_NCHANNELS", "1")
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
@@ -590,7 +618,8 @@ def main():
     if args.impl == "reference":
         line = run_reference(args, rank, world, dev)
         if line is not None:
-            print(json.dumps(line))
+            json_out.write(json.dumps(line) + "\n")
+            json_out.flush()
         return
 
     if world > 1:
@@ -599,7 +628,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     line = run_ours(args, rank, world, dev)
     if rank == 0 and line is not None:
-        print(json.dumps(line))
+        json_out.write(json.dumps(line) + "\n")
+        json_out.flush()
     if world > 1:
         import torch.distributed as dist
         dist.barrier()

@@ -193,6 +193,15 @@ int mc_mlp_rows(int numRows, const int* dNumRows, int numLayers, const int* dims
                 const float* t0, int relu0, const float* const* W, const float* const* bias,
                 const float* const* scale, const float* const* shift, const int* relu, float* y, void* stream);
 
+/* ---- multi-GPU: the one collective of a sharded step, over NVLink peer memory (no NCCL on the data path) ----------
+ * All-gather of floatsPerRank floats per rank through symmetric buffers mapped on every peer: peer stores + flag
+ * words, one CTA, capturable in a CUDA graph.  peerBufPtrs: device array of worldSize buffer addresses (64-bit ints),
+ * each buffer mc_allgather_rows_p2p_buffer_floats() floats, zero-filled before the first step; stepCounter: device
+ * int, zero before the first step.  (The reference has no multi-GPU path; BASELINE.json's north_star prescribes it.) */
+long long mc_allgather_rows_p2p_buffer_floats(int floatsPerRank, int worldSize);
+int mc_allgather_rows_p2p(int floatsPerRank, int rank, int worldSize, const float* local, const long long* peerBufPtrs,
+                          int* stepCounter, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

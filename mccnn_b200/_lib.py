@@ -62,6 +62,8 @@ SIGNATURES = {
     "mc_spatial_conv_grad": (_c_int, [_c_int] * 8 + [_c_float, _c_int] + [_ptr] * 25),
     "mc_sort_points_step2_grad": (_c_int, [_c_int, _c_int] + [_ptr] * 6),
     "mc_get_sampled_features_grad": (_c_int, [_c_int, _c_int, _c_int] + [_ptr] * 4),
+    "mc_allgather_rows_p2p_buffer_floats": (_c_ll, [_c_int, _c_int]),
+    "mc_allgather_rows_p2p": (_c_int, [_c_int, _c_int, _c_int, _ptr, _ptr, _ptr, _ptr, _ptr]),
 }
 
 

@@ -417,6 +417,42 @@ def gather_logits(local_logits, batch_size, world_size, group=None):
     return torch.cat(pieces, dim=0)
 
 
+class PeerGather:
+    """gather_logits for equal shards over NVLink PEER MEMORY instead of NCCL (csrc/peer_gather.cu): every rank stores
+    its [rows, cols] logits straight into a symmetric buffer on every peer and waits on flag words -- one tiny kernel
+    that is captured into the forward's CUDA graph like any other node.  One instance per concurrent lane.
+
+    The symmetric buffers come from torch.distributed._symmetric_memory (CUDA VMM allocations exported to the peers of
+    `group`); construction is collective.  Raises if symmetric memory is unavailable (caller falls back to NCCL)."""
+
+    def __init__(self, rows, cols, device, group=None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        from ._lib import lib
+        group = dist.group.WORLD if group is None else group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.rows, self.cols, self.n = rows, cols, rows * cols
+        floats = int(lib.mc_allgather_rows_p2p_buffer_floats(self.n, self.world))
+        self.buf = symm.empty((floats,), dtype=torch.float32, device=device)
+        self.buf.zero_()
+        torch.cuda.synchronize(device)            # my flags are zero before any peer can learn my address
+        self.handle = symm.rendezvous(self.buf, group)
+        ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        if len(ptrs) != self.world or any(p == 0 for p in ptrs):
+            raise RuntimeError("symmetric memory rendezvous returned no peer addresses")
+        self.ptrs = torch.tensor(ptrs, dtype=torch.int64, device=device)
+        self.counter = torch.zeros((1,), dtype=torch.int32, device=device)
+        dist.barrier(group)
+
+    def __call__(self, local_logits):
+        from . import ops
+        if tuple(local_logits.shape) != (self.rows, self.cols):
+            raise ValueError("PeerGather: expected logits of shape %s" % ((self.rows, self.cols),))
+        out = local_logits.new_empty((self.world * self.rows, self.cols))
+        ops.allgather_rows_p2p(local_logits, self.ptrs, self.counter, self.rank, self.world, out)
+        return out
+
+
 def gather_point_logits(local_logits, world_size, group=None):
     """Segmentation variant of the closing collective: per-point logits [N_r, F] with a
     different N_r on every rank.  ONE all_gather: every rank contributes a block padded to the largest N_r whose first

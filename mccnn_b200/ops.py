@@ -345,3 +345,11 @@ def mlp_rows(x, layers, pre=None, pre_relu=False, n_dev=None):
     check(lib.mc_mlp_rows(x.shape[0], _p(n_dev), n, D, _p(x), _p(s0), _p(t0), int(bool(pre_relu)), W, B, S, T, R,
                           _p(y), _stream()))
     return y
+
+
+def allgather_rows_p2p(local, peer_ptrs, counter, rank, world, out):
+    """All-gather of `local` (same numel on every rank) through symmetric peer buffers (csrc/peer_gather.cu)."""
+    local = _f(local)
+    check(lib.mc_allgather_rows_p2p(local.numel(), int(rank), int(world), _p(local), _p(peer_ptrs), _p(counter),
+                                    _p(out), _stream()))
+    return out

@@ -201,3 +201,48 @@ def test_mcclasss_matches_oracle_pipeline():
     assert got.shape == want.shape
     denom = np.abs(want).max()
     assert np.abs(got - want).max() <= 2e-4 * denom, np.abs(got - want).max() / denom
+
+
+def test_peer_gather_single_rank_group():
+    """engine.PeerGather (csrc/peer_gather.cu, the NVLink peer-memory all-gather that closes a sharded step) on a
+    one-rank process group: the same kernel, symmetric-memory rendezvous and CUDA-graph capture as on N GPUs, with the
+    rank as its own only peer.  (The N > 1 exchange is exercised by tools/peer_gather_check.py under torchrun and by
+    bench.py --gpus N; the driver's GPU test tier has one GPU.)"""
+    import os
+    import torch
+    import torch.distributed as dist
+    from mccnn_b200.engine import PeerGather
+    dev = torch.device("cuda:0")
+    created = False
+    if not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29533")
+        try:
+            dist.init_process_group("nccl", rank=0, world_size=1, device_id=dev)
+        except Exception as exc:  # noqa: BLE001
+            pytest.skip("no process group on this box: %r" % (exc,))
+        created = True
+    try:
+        try:
+            pg = PeerGather(8, 40, dev)
+        except Exception as exc:  # noqa: BLE001
+            pytest.skip("symmetric memory unavailable on this box: %r" % (exc,))
+        x = torch.arange(320, dtype=torch.float32, device=dev).reshape(8, 40)
+        for step in range(5):
+            assert torch.equal(pg(x + step), x + step)
+        xs = x.clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            pg(xs)
+        torch.cuda.current_stream().wait_stream(side)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            out = pg(xs)
+        for step in range(5):
+            xs.fill_(float(step))
+            g.replay()
+            assert torch.equal(out, xs)
+    finally:
+        if created:
+            dist.destroy_process_group()
