@@ -52,7 +52,23 @@ def _dense(x, w, b, pre=None, **kw):
             w, b = _fold_into_weights(pre, w, b)
         pre, pre_relu, x = (x.scale, x.shift), x.relu, x.base
     nd, h = _cnt(x), _hint(x)
+    if x.shape[0] * w.shape[0] * w.shape[1] >= _LIBRARY_GEMM_MACS and not kw:
+        return _tag(_dense_library(x, w, b, pre, pre_relu, nd), nd, h)
     return _tag(ops.dense_layer(x, w, b, pre=pre, pre_relu=pre_relu, n_dev=nd, rows_hint=h, **kw), nd, h)
+
+
+# The dense.cu kernels are built for the latency-bound sizes of the classification networks (a few thousand rows,
+# widths <= 512).  The segmentation networks run the same 1x1 layers over every input point (MCSeg: 131 072 rows x 832
+# -> 256 = 28 GMAC): a plain large FP32 GEMM, which goes to cuBLAS (torch.addmm) exactly as the reference sends it to
+# TensorFlow's matmul; the folded batch norm + ReLU in front of it stays one own elementwise launch.
+_LIBRARY_GEMM_MACS = 1 << 30
+
+
+def _dense_library(x, w, b, pre, pre_relu, nd):
+    def run():
+        a = x if pre is None else ops.scale_shift_act(x, pre[0], pre[1], pre_relu, nd)
+        return torch.addmm(b, a, w)
+    return _dispatch([x], run)
 
 
 def _mlp(x, layers, pre=None):
