@@ -61,7 +61,7 @@ def _dense(x, w, b, pre=None, **kw):
 # widths <= 512).  The segmentation networks run the same 1x1 layers over every input point (MCSeg: 131 072 rows x 832
 # -> 256 = 28 GMAC): a plain large FP32 GEMM, which goes to cuBLAS (torch.addmm) exactly as the reference sends it to
 # TensorFlow's matmul; the folded batch norm + ReLU in front of it stays one own elementwise launch.
-_LIBRARY_GEMM_MACS = 1 << 30
+_LIBRARY_GEMM_MACS = 1 << 27
 
 
 def _dense_library(x, w, b, pre, pre_relu, nd):

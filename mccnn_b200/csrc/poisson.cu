@@ -23,6 +23,8 @@
 #include "common.cuh"
 #include "lookback.cuh"
 
+#include <algorithm>
+
 namespace mc {
 namespace {
 
@@ -34,6 +36,11 @@ constexpr int kSelfOffset = 17;           // index of (0,0,0) in kOffsPool
 constexpr int kCellListCap = 8192;        // cells per cloud up to which the per-phase non-empty cell lists are built
 constexpr int kStageCells = 4096;         // cell-table rows of a cloud staged in shared memory up to this many cells
 constexpr int kStagePts = 4096;           // points of a cloud staged in shared memory up to this many points
+#ifdef MCCNN_POISSON_SINGLE_LAUNCH
+constexpr bool kForceSingleLaunch = true;  // build-time switch: one CTA per cloud also on fine grids (A/B timing)
+#else
+constexpr bool kForceSingleLaunch = false;
+#endif
 
 // phase (index into kOffsPool) of the offset (ox, oy, oz), indexed by (ox+1)*9 + (oy+1)*3 + (oz+1)
 __device__ __constant__ const unsigned char kPhaseOfOffset[27] = {
@@ -215,7 +222,9 @@ __global__ void __launch_bounds__(kSelThreads)
                    const float* __restrict__ mx, const float* __restrict__ pts, const int2* __restrict__ cellIdx,
                    unsigned char* selGlobal, int* __restrict__ tmpIdx, unsigned long long* chain, int capOut,
                    float* __restrict__ outPts, int* __restrict__ outBids, int* __restrict__ outIdx,
-                   int* __restrict__ dNumSamples, int* __restrict__ dOverflow) {
+                   int* __restrict__ dNumSamples, int* __restrict__ dOverflow, bool phasesDone) {
+    // phasesDone: the accepted flags were already produced in selGlobal by the many-CTA phase kernels (fine grids);
+    // this launch then only orders and writes the samples
     extern __shared__ __align__(16) unsigned char smemRaw[];
     SelShared& sh = *reinterpret_cast<SelShared*>(smemRaw);
     unsigned char* sFlags = smemRaw + sizeof(SelShared);
@@ -243,8 +252,8 @@ __global__ void __launch_bounds__(kSelThreads)
     const int b = sh.cloud;
     const int cellsPerCloud = n * n * n;
     const int2* cells = cellIdx + (size_t)b * cellsPerCloud;
-    const bool useLists = cellsPerCloud <= kCellListCap;
-    const bool stageCells = cellsPerCloud <= kStageCells;
+    const bool useLists = cellsPerCloud <= kCellListCap && !phasesDone;
+    const bool stageCells = cellsPerCloud <= kStageCells && !phasesDone;
 
     // extent of this cloud inside the sorted array (the sort is batch-major) + non-empty cells per phase
     {
@@ -275,12 +284,12 @@ __global__ void __launch_bounds__(kSelThreads)
     __syncthreads();
     const int cLo = sh.lo, cHi = sh.hi;
     const int nCloud = cHi > cLo ? cHi - cLo : 0;
-    const bool inSmem = nCloud <= kSelFlagBytes;
+    const bool inSmem = nCloud <= kSelFlagBytes && !phasesDone;
     if (inSmem)
         for (int t = threadIdx.x; t < nCloud; t += kSelThreads) sFlags[t] = 0;
     // every later access to the cloud's points and cell rows is then a shared-memory access: the per-cell work is a
     // chain of dependent loads, and first-touch global misses were what made it slow
-    const bool stagePts = nCloud <= kStagePts;
+    const bool stagePts = nCloud <= kStagePts && !phasesDone;
     if (stagePts)
         for (int t = threadIdx.x; t < nCloud * 3; t += kSelThreads) sPts[t] = pts[(size_t)cLo * 3 + t];
     if (useLists) {
@@ -324,7 +333,7 @@ __global__ void __launch_bounds__(kSelThreads)
 
     const float invN = 1.0f / (float)n, invNN = 1.0f / (float)(n * n);
     if (nCloud > 0) {
-        for (int ph = 0; ph < 27; ++ph) {
+        for (int ph = 0; ph < 27 && !phasesDone; ++ph) {
             if (useLists) {
                 const int beg = sh.phaseCellStart[ph], end = sh.phaseCellStart[ph + 1];
                 for (int t = beg + warp; t < end; t += kSelWarps) {
@@ -422,6 +431,82 @@ __global__ void __launch_bounds__(kSelThreads)
     }
 }
 
+// ---- fine grids (more than kCellListCap cells per cloud: MCSeg's r = 0.025 levels, ScanNet rooms) ----------------
+// One CTA per cloud would walk tens of thousands of mostly empty cells per phase with 16 warps (measured: 14 ms for
+// 8 rooms x 80 000 points).  Instead the non-empty cells of the whole batch are listed per phase once, and every phase
+// is ONE launch over its list with a warp per cell across the whole GPU; the accepted flags live in global memory
+// (selGlobal) and kernel boundaries order the phases.  The same process_cell does the work; poisson_kernel with
+// phasesDone = true then orders and writes the samples.
+__global__ void __launch_bounds__(256) poisson_list_cells_kernel(int totalCells, int n, bool fill,
+                                                                 const int2* __restrict__ cellIdx,
+                                                                 int* __restrict__ phaseCount,   // [27] counts
+                                                                 int* __restrict__ phaseFill,    // [27] cursors
+                                                                 int* __restrict__ cellList) {
+    __shared__ unsigned char sPhaseOf[27];
+    __shared__ int sStart[28];
+    if (threadIdx.x < 27) sPhaseOf[threadIdx.x] = kPhaseOfOffset[threadIdx.x];
+    if (fill && threadIdx.x == 0) {
+        int run = 0;
+        for (int p = 0; p < 27; ++p) {
+            sStart[p] = run;
+            run += phaseCount[p];
+        }
+    }
+    __syncthreads();
+    const int cellsPerCloud = n * n * n;
+    for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < totalCells; g += gridDim.x * blockDim.x) {
+        const int2 ce = cellIdx[g];
+        if (ce.y <= ce.x) continue;
+        const int c = g % cellsPerCloud;
+        const int x = c / (n * n), y = (c / n) % n, z = c % n;
+        const int p = sPhaseOf[(x % 3) * 9 + (y % 3) * 3 + (z % 3)];
+        if (!fill)
+            atomicAdd(&phaseCount[p], 1);
+        else
+            cellList[sStart[p] + atomicAdd(&phaseFill[p], 1)] = g;
+    }
+}
+
+__global__ void __launch_bounds__(kSelThreads)
+    poisson_phase_kernel(int ph, bool scaleInv, float radius, int n, const float* __restrict__ mn,
+                         const float* __restrict__ mx, const float* __restrict__ pts, const int2* __restrict__ cellIdx,
+                         unsigned char* selGlobal, const int* __restrict__ phaseCount,
+                         const int* __restrict__ cellList) {
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    SelShared& sh = *reinterpret_cast<SelShared*>(smemRaw);
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    int beg = 0;
+    for (int p = 0; p < ph; ++p) beg += phaseCount[p];
+    const int end = beg + phaseCount[ph];
+    const int cellsPerCloud = n * n * n;
+    CloudCtx cx;
+    cx.sCells = nullptr;
+    cx.pts = pts;
+    cx.sPts = nullptr;
+    cx.sAccIdx = nullptr;
+    cx.sAccCnt = nullptr;
+    cx.sFlags = nullptr;
+    cx.gFlags = selGlobal;
+    cx.cLo = 0;
+    cx.n = n;
+    cx.offX = lane < 27 ? kOffsPool[lane][0] : 0;
+    cx.offY = lane < 27 ? kOffsPool[lane][1] : 0;
+    cx.offZ = lane < 27 ? kOffsPool[lane][2] : 0;
+    int cloud = -1;
+    for (int t = beg + blockIdx.x * kSelWarps + warp; t < end; t += gridDim.x * kSelWarps) {
+        const int g = cellList[t];
+        const int b = g / cellsPerCloud, c = g - b * cellsPerCloud;
+        if (b != cloud) {  // per-cloud frame: cell rows and the exact squared-radius threshold
+            cloud = b;
+            cx.cells = cellIdx + (size_t)b * cellsPerCloud;
+            const float ext = max_extent(mn, mx, b);
+            cx.thr = exact_radius_threshold(scaleInv ? __fmul_rn(radius, ext) : radius);
+        }
+        const int x = c / (n * n), rem = c - x * n * n, y = rem / n, z = rem - y * n;
+        process_cell(cx, sh, warp, lane, c, x, y, z, cx.cells[c], ph);
+    }
+}
+
 constexpr size_t kSelSmemBytes = sizeof(SelShared) + kSelFlagBytes + kCellListCap * sizeof(unsigned short) +
                                  kStageCells * sizeof(int2) + kStagePts * 3 * sizeof(float) +
                                  kStagePts * sizeof(unsigned short) + kStageCells;
@@ -431,10 +516,10 @@ constexpr size_t kSelSmemBytes = sizeof(SelShared) + kSelFlagBytes + kCellListCa
 
 using namespace mc;
 
-// workspace ints: look-back descriptors (2 * (B + 2)) | flag bytes (N/4 + 1 ints) | tmpIdx[N]
+// workspace ints: look-back descriptors (2 * (B + 2)) | flag bytes (N/4 + 1 ints) | tmpIdx[N] | 64 counters | list[N]
 extern "C" long long mc_poisson_workspace_ints(int numPoints, int batchSize) {
     long long N = numPoints > 0 ? numPoints : 1;
-    return 2LL * (batchSize + 2) + (N / 4 + 1) + N + 8;
+    return 2LL * (batchSize + 2) + (N / 4 + 1) + N + 8 + (N + 64);  // ... | phase counters / cursors | cell list
 }
 
 // samplePointCloud + copyPoints, tf_ops/poisson_sampling.cu:175-244.  Outputs hold capacityOut rows (numPoints
@@ -465,10 +550,33 @@ extern "C" int mc_poisson_sampling(int scaleInv, float radius, int numPoints, co
     unsigned char* sel = reinterpret_cast<unsigned char*>(workspace + descInts);
     int* tmpIdx = workspace + descInts + (N / 4 + 1);
     cudaMemsetAsync(workspace, 0, sizeof(int) * (size_t)(descInts + (N / 4 + 1)), s);  // descriptors + flags
+    const long long cellsPerCloud = (long long)numCells * numCells * numCells;
+    const bool fineGrid = cellsPerCloud > kCellListCap && !kForceSingleLaunch;
+    if (numPoints > 0 && fineGrid) {
+        // non-empty cells of the batch per phase, then one launch per phase over the whole GPU
+        MC_REQUIRE(cellsPerCloud * batchSize < (1LL << 31), "mc_poisson_sampling: cell table too large");
+        const int totalCells = (int)(cellsPerCloud * batchSize);
+        int* counters = tmpIdx + N;          // [0..27) counts, [32..59) cursors
+        int* cellList = counters + 64;       // <= numPoints non-empty cells
+        cudaMemsetAsync(counters, 0, sizeof(int) * 64, s);
+        const int listGrid = std::min(cdiv(totalCells, 256), 148 * 8);
+        const int2* cells2 = reinterpret_cast<const int2*>(cellIdx);
+        poisson_list_cells_kernel<<<listGrid, 256, 0, s>>>(totalCells, numCells, false, cells2, counters,
+                                                           counters + 32, cellList);
+        poisson_list_cells_kernel<<<listGrid, 256, 0, s>>>(totalCells, numCells, true, cells2, counters,
+                                                           counters + 32, cellList);
+        // a warp per listed cell; the list length is only known on the device: a grid that covers the GPU a few
+        // times over and strides (at most numPoints / 27 cells per phase on average)
+        const int phaseGrid = std::max(1, std::min(cdiv(cdiv(numPoints, 8), kSelWarps), 148 * 4));
+        for (int ph = 0; ph < 27; ++ph)
+            poisson_phase_kernel<<<phaseGrid, kSelThreads, sizeof(SelShared), s>>>(
+                ph, scaleInv != 0, radius, numCells, aabbMin, aabbMax, pts, cells2, sel, counters, cellList);
+        count_launches(29);
+    }
     if (numPoints > 0) {
         poisson_kernel<<<batchSize, kSelThreads, kSelSmemBytes, s>>>(
             scaleInv != 0, radius, batchSize, numCells, aabbMin, aabbMax, pts, reinterpret_cast<const int2*>(cellIdx),
-            sel, tmpIdx, chain, capacityOut, outPts, outBatchIds, outIdx, dNumSamples, dOverflow);
+            sel, tmpIdx, chain, capacityOut, outPts, outBatchIds, outIdx, dNumSamples, dOverflow, fineGrid);
     } else {
         cudaMemsetAsync(dNumSamples, 0, sizeof(int), s);
     }
