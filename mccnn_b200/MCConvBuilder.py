@@ -72,6 +72,10 @@ class PointHierarchy:
         self.batchSize_ = batchSize
         self.relativeRadius_ = relativeRadius
         self.hierarchyName_ = hierarchyName
+        # grids the hierarchy sorted for its own sampling, keyed (level, cell size, relative): a convolution on the
+        # same level with the same radius reuses them instead of sorting again (not in the reference, which re-sorts;
+        # the result is the same grid)
+        self.levelGrids_ = {}
 
         with _rt.lane("hier"):  # the hierarchy chain runs on its own stream in planned mode
             self._build(inPoints, inBatchIds, radiusList, batchSize)
@@ -103,6 +107,8 @@ class PointHierarchy:
             sampledPts, sampledBatchsIds, sampledIndexs = poisson_sampling(
                 sortPts, sortBatchs, cellIndexs, aabbMin, aabbMax, currRadius, batchSize, self.relativeRadius_)
 
+            self.levelGrids_[(level, currRadius, bool(self.relativeRadius_))] = (sortPts, sortBatchs, cellIndexs,
+                                                                                indexs)
             self.points_.append(sampledPts)
             self.batchIds_.append(sampledBatchsIds)
             self.features_.append_lazy(
@@ -180,6 +186,9 @@ class ConvolutionBuilder:
 
     def _geometry(self, ph, inPointLevel, currOutPointHierarchy, currOutPointLevel, convRadius, currRelativeRadius,
                   currKDEWindow, currUsePDF, keyGrid, keyNeighs, keyPDF):
+        shared = getattr(ph, "levelGrids_", {}).get((inPointLevel, convRadius, bool(currRelativeRadius)))
+        if keyGrid not in self.cacheGrids_ and shared is not None:
+            self.cacheGrids_[keyGrid] = shared
         if keyGrid not in self.cacheGrids_:
             # sort_points_step1 + sort_points_step2 (utils/MCConvBuilder.py:353-361), fused into one launch.  The grid
             # is pure geometry (it does not depend on the features), so it is built without them and the features
