@@ -18,6 +18,7 @@ namespace mc {
 namespace {
 
 constexpr int kDnBM = 32, kDnBN = 64, kDnBK = 32, kDnThreads = 256;
+constexpr int kRowThreads = 1024;  // row kernels: the K loop of a layer is a chain of L2 round trips -- many short slices
 constexpr int kRowsMaxK = 1024;  // dense_rows_kernel keeps one activated input row in shared memory
 
 __global__ void __launch_bounds__(256) scale_shift_act_kernel(const int* __restrict__ dRows, int capRows, int cols,
@@ -47,9 +48,9 @@ __device__ __forceinline__ float epilogue(float v, int c, const float* __restric
 __device__ __forceinline__ void row_layer(const float* sA, float* sPart, int K, int N, const float* __restrict__ W,
                                           const float* __restrict__ bias, const float* __restrict__ s2,
                                           const float* __restrict__ t2, int relu2, float* out) {
-    for (int c0 = 0; c0 < N; c0 += kDnThreads) {
-        const int cols = min(N - c0, kDnThreads);
-        const int slices = kDnThreads / cols;
+    for (int c0 = 0; c0 < N; c0 += kRowThreads) {
+        const int cols = min(N - c0, kRowThreads);
+        const int slices = kRowThreads / cols;
         const int c = threadIdx.x % cols, s = threadIdx.x / cols;
         float acc = 0.0f;
         if (s < slices) {
@@ -83,7 +84,7 @@ __device__ __forceinline__ void row_layer(const float* sA, float* sPart, int K, 
 
 __device__ __forceinline__ void load_row(float* sA, int K, const float* __restrict__ x, const float* __restrict__ s1,
                                          const float* __restrict__ t1, int relu1) {
-    for (int k = threadIdx.x; k < K; k += kDnThreads) {
+    for (int k = threadIdx.x; k < K; k += kRowThreads) {
         float v = x[k];
         if (s1 != nullptr) v = fmaf(v, s1[k], t1[k]);
         sA[k] = relu1 ? fmaxf(v, 0.0f) : v;
@@ -92,13 +93,13 @@ __device__ __forceinline__ void load_row(float* sA, int K, const float* __restri
 }
 
 // one CTA per row, one layer
-__global__ void __launch_bounds__(kDnThreads)
+__global__ void __launch_bounds__(kRowThreads)
     dense_rows_kernel(const int* __restrict__ dRows, int capRows, int K, int N, const float* __restrict__ x,
                       const float* __restrict__ s1, const float* __restrict__ t1, int relu1,
                       const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ s2,
                       const float* __restrict__ t2, int relu2, float* __restrict__ y) {
     __shared__ float sA[kRowsMaxK];
-    __shared__ float sPart[kDnThreads];
+    __shared__ float sPart[kRowThreads];
     const int rows = live_count(dRows, capRows);
     const int r = blockIdx.x;
     if (r >= rows) return;
@@ -119,12 +120,12 @@ struct MlpArgs {
     int relu[kMlpMaxLayers];
 };
 
-__global__ void __launch_bounds__(kDnThreads)
+__global__ void __launch_bounds__(kRowThreads)
     mlp_rows_kernel(const int* __restrict__ dRows, int capRows, const float* __restrict__ x,
                     const float* __restrict__ s0, const float* __restrict__ t0, int relu0, const MlpArgs a,
                     float* __restrict__ y) {
     __shared__ float sBuf[2][kRowsMaxK];
-    __shared__ float sPart[kDnThreads];
+    __shared__ float sPart[kRowThreads];
     const int rows = live_count(dRows, capRows);
     const int r = blockIdx.x;
     if (r >= rows) return;
@@ -238,7 +239,7 @@ extern "C" int mc_dense_layer(int numRows, const int* dNumRows, int numRowsHint,
     cudaStream_t s = (cudaStream_t)stream;
     const int live = (numRowsHint > 0 && numRowsHint < numRows) ? numRowsHint : numRows;
     if (live <= 128 && K <= kRowsMaxK) {
-        dense_rows_kernel<<<numRows, kDnThreads, 0, s>>>(dNumRows, numRows, K, N, x, s1, t1, relu1, W, bias, s2, t2,
+        dense_rows_kernel<<<numRows, kRowThreads, 0, s>>>(dNumRows, numRows, K, N, x, s1, t1, relu1, W, bias, s2, t2,
                                                           relu2, y);
     } else {
         dim3 grid(cdiv(numRows, kDnBM), cdiv(N, kDnBN));
@@ -274,6 +275,6 @@ extern "C" int mc_mlp_rows(int numRows, const int* dNumRows, int numLayers, cons
         a.relu[l] = relu[l];
     }
     if (numRows <= 0) return 0;
-    mlp_rows_kernel<<<numRows, kDnThreads, 0, (cudaStream_t)stream>>>(dNumRows, numRows, x, s0, t0, relu0, a, y);
+    mlp_rows_kernel<<<numRows, kRowThreads, 0, (cudaStream_t)stream>>>(dNumRows, numRows, x, s0, t0, relu0, a, y);
     return check_launch("mc_mlp_rows");
 }

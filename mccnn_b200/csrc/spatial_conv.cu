@@ -412,6 +412,11 @@ __global__ void __launch_bounds__(256) combine_kernel(const int* __restrict__ dM
     out[t] = acc;
 }
 
+int env_int(const char* name, int dflt) {
+    const char* v = std::getenv(name);
+    return v ? std::atoi(v) : dflt;
+}
+
 constexpr int kChunkBlocks = 4;  // MLP blocks per warp (fewer when the convolution has fewer)
 
 // blocks past the end of the parameter arrays are evaluated with zero parameters (no branch in the tile loop, so the
@@ -419,7 +424,11 @@ constexpr int kChunkBlocks = 4;  // MLP blocks per warp (fewer when the convolut
 template <int MODE>
 void launch_conv(const ConvArgs& a, int nb, int G, cudaStream_t s) {
     const int runs = cdiv(a.capM, G);
-    if (nb >= 3) {
+    static const int forcedNB = env_int("MCCNN_CONV_NB", 0);  // tuning knob: MLP blocks per warp (2 or 4), 0 = default
+    if (nb >= 3 && forcedNB == 2) {
+        dim3 grid(cdiv(runs, kConvWarps), cdiv(nb, 2));
+        spatial_conv_kernel<MODE, 2><<<grid, kConvWarps * 32, 0, s>>>(a);
+    } else if (nb >= 3) {
         dim3 grid(cdiv(runs, kConvWarps), cdiv(nb, 4));
         spatial_conv_kernel<MODE, 4><<<grid, kConvWarps * 32, 0, s>>>(a);
     } else if (nb == 2) {
@@ -429,11 +438,6 @@ void launch_conv(const ConvArgs& a, int nb, int G, cudaStream_t s) {
         dim3 grid(cdiv(runs, kConvWarps), 1);
         spatial_conv_kernel<MODE, 1><<<grid, kConvWarps * 32, 0, s>>>(a);
     }
-}
-
-int env_int(const char* name, int dflt) {
-    const char* v = std::getenv(name);
-    return v ? std::atoi(v) : dflt;
 }
 
 }  // namespace
