@@ -50,6 +50,36 @@ __device__ __constant__ const unsigned char kPhaseOfOffset[27] = {
     /*(1,-1,-1)*/ 13,  /*(1,-1,0)*/ 21,  /*(1,-1,1)*/ 9,   /*(1,0,-1)*/ 20,  /*(1,0,0)*/ 8,   /*(1,0,1)*/ 10,
     /*(1,1,-1)*/ 0,    /*(1,1,0)*/ 19,   /*(1,1,1)*/ 23};
 
+// ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) of one contiguous global range into shared memory, completion on an
+// mbarrier: used to stage a cloud's points -- one asynchronous copy issued by one thread instead of a strided loop of
+// 4-byte loads by the whole CTA.  Addresses and size must be multiples of 16 bytes.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dstSmem, const void* srcGlobal, unsigned bytes,
+                                              unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dstSmem)),
+                 "l"(srcGlobal), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "MC_MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra MC_MBAR_DONE;\n"
+        "bra MC_MBAR_WAIT;\n"
+        "MC_MBAR_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
 struct SelShared {
     float4 list[kSelWarps][kListCap];
     int listIdx[kSelWarps][kListCap];
@@ -60,6 +90,7 @@ struct SelShared {
     int phaseCellStart[28];  // non-empty cell lists: cells of phase p are cellList[phaseCellStart[p] .. [p+1])
     int phaseCellFill[27];
     int lo, hi, cloud, base;
+    unsigned long long stageBar;  // mbarrier of the bulk copy that stages the cloud's points
 };
 
 struct CloudCtx {
@@ -230,8 +261,8 @@ __global__ void __launch_bounds__(kSelThreads)
     unsigned char* sFlags = smemRaw + sizeof(SelShared);
     unsigned short* cellList = reinterpret_cast<unsigned short*>(sFlags + kSelFlagBytes);
     int2* sCells = reinterpret_cast<int2*>(sFlags + kSelFlagBytes + kCellListCap * sizeof(unsigned short));
-    float* sPts = reinterpret_cast<float*>(sCells + kStageCells);
-    unsigned short* sAccIdx = reinterpret_cast<unsigned short*>(sPts + kStagePts * 3);
+    float* sPts = reinterpret_cast<float*>(sCells + kStageCells);  // + 16 bytes of slack for the alignment shift
+    unsigned short* sAccIdx = reinterpret_cast<unsigned short*>(sPts + kStagePts * 3 + 4);
     unsigned char* sAccCnt = reinterpret_cast<unsigned char*>(sAccIdx + kStagePts);
     const int lane = lane_id(), warp = threadIdx.x >> 5;
     const unsigned ltMask = (1u << lane) - 1u;
@@ -241,6 +272,7 @@ __global__ void __launch_bounds__(kSelThreads)
         sh.cloud = lookback_ticket(chain);
         sh.lo = INT_MAX;
         sh.hi = 0;
+        mbar_init(&sh.stageBar, 1);
     }
     if (threadIdx.x < 28) {
         sh.phaseBase[threadIdx.x] = 0;
@@ -290,8 +322,26 @@ __global__ void __launch_bounds__(kSelThreads)
     // every later access to the cloud's points and cell rows is then a shared-memory access: the per-cell work is a
     // chain of dependent loads, and first-touch global misses were what made it slow
     const bool stagePts = nCloud <= kStagePts && !phasesDone;
-    if (stagePts)
-        for (int t = threadIdx.x; t < nCloud * 3; t += kSelThreads) sPts[t] = pts[(size_t)cLo * 3 + t];
+    if (stagePts) {
+        // the cloud's points are one contiguous range of 12-byte rows: the 16-byte aligned interior goes through ONE
+        // TMA bulk copy, the (at most 12 + 12) bytes before / after it through plain loads; the shared-memory image
+        // is shifted by the same misalignment so that both sides of the bulk copy are 16-byte aligned
+        const char* gsrc = reinterpret_cast<const char*>(pts + (size_t)cLo * 3);
+        const unsigned bytes = (unsigned)nCloud * 12u;
+        const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(gsrc) & 15u);
+        char* sdst = reinterpret_cast<char*>(sPts) + mis;
+        const unsigned head = mis ? min(16u - mis, bytes) : 0u;
+        const unsigned bulk = ((bytes - head) / 16u) * 16u;
+        const unsigned tail = bytes - head - bulk;
+        if (threadIdx.x == 0 && bulk > 0) bulk_copy_g2s(sdst + head, gsrc + head, bulk, &sh.stageBar);
+        if (threadIdx.x >= 32 && threadIdx.x < 32 + (head + tail) / 4) {
+            const unsigned e = threadIdx.x - 32;
+            const unsigned off = e < head / 4 ? e * 4 : head + bulk + (e - head / 4) * 4;
+            *reinterpret_cast<float*>(sdst + off) = *reinterpret_cast<const float*>(gsrc + off);
+        }
+        sPts = reinterpret_cast<float*>(sdst);
+        if (bulk > 0) mbar_wait(&sh.stageBar, 0);
+    }
     if (useLists) {
         if (threadIdx.x == 0) {
             int run = 0;
@@ -508,7 +558,7 @@ __global__ void __launch_bounds__(kSelThreads)
 }
 
 constexpr size_t kSelSmemBytes = sizeof(SelShared) + kSelFlagBytes + kCellListCap * sizeof(unsigned short) +
-                                 kStageCells * sizeof(int2) + kStagePts * 3 * sizeof(float) +
+                                 kStageCells * sizeof(int2) + (kStagePts * 3 + 4) * sizeof(float) +
                                  kStagePts * sizeof(unsigned short) + kStageCells;
 
 }  // namespace
