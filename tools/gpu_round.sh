@@ -24,5 +24,5 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --
 python tools/launch_summary.py $out/launches_bench.csv > $out/launches_bench.summary.txt 2>&1; head -30 $out/launches_bench.summary.txt
 echo "== ncu full capture of the hot kernels"
 timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on \
-    -k regex:"spatial_conv|poisson_kernel|neighbors" -c 12 -o $out/prof_hot -f python tools/ncu_target.py --forwards 1 > $out/ncu_full.log 2>&1
+    -c 30 -o $out/prof_hot -f python tools/ncu_target.py --forwards 1 > $out/ncu_full.log 2>&1
 ls -la $out

@@ -26,7 +26,7 @@ def main(path):
         for i, n in cols:
             v = r[i]
             if n == "kernel":
-                v = v.replace("void ", "").replace("unnamed>::", "").split("(")[0][:34]
+                v = v.replace("void ", "").replace("mc::<unnamed>::", "").replace("unnamed>::", "").split("(")[0][:34]
             elif n in ("dram_rd", "dram_wr"):
                 v = "%.0f B" % (float(v.replace(",", "")) * SCALE.get(units[i], 1.0))
             else:
