@@ -147,10 +147,11 @@ __device__ __forceinline__ void process_cell(const CloudCtx& cx, SelShared& sh, 
     if (cx.sAccIdx != nullptr) {
         // per-cell accepted lists: a lane copies the (few) accepted points of its neighbour cell, placed by a warp scan
         const int cntL = ncell >= 0 ? cx.sAccCnt[ncell] : 0;
-        const int incl = warp_inclusive_scan(cntL);
+        // no accepted neighbour at all (every cell of the early phases): skip the scan and the copy
+        const int incl = __any_sync(MC_FULL_MASK, cntL > 0) ? warp_inclusive_scan(cntL) : 0;
         L = __shfl_sync(MC_FULL_MASK, incl, 31);
         listOk = L <= kListCap;
-        if (listOk) {
+        if (listOk && L > 0) {
             const int pos = incl - cntL;
             for (int k = 0; k < cntL; ++k) {
                 float qx, qy, qz;
@@ -185,8 +186,7 @@ __device__ __forceinline__ void process_cell(const CloudCtx& cx, SelShared& sh, 
     for (int c0 = own.x; c0 < own.y; c0 += 32) {
         const int cnt = min(32, own.y - c0);
         // lanes spread over (point, list slice): pointLanes = smallest power of two >= cnt
-        int pointLanes = 1;
-        while (pointLanes < cnt) pointLanes <<= 1;
+        const int pointLanes = cnt > 1 ? 1 << (32 - __clz(cnt - 1)) : 1;
         const int slices = 32 / pointLanes;
         const int pi = lane & (pointLanes - 1), slice = lane / pointLanes;
         const int i = c0 + pi;
@@ -214,7 +214,13 @@ __device__ __forceinline__ void process_cell(const CloudCtx& cx, SelShared& sh, 
                     }
             }
         }
-        for (int off = pointLanes; off < 32; off <<= 1) blocked |= __shfl_xor_sync(MC_FULL_MASK, blocked, off);
+        {   // OR over the slices of a point: one ballot, then the bits of the lanes that share this lane's point
+            // (positions pi, pi + pointLanes, ...) -- instead of log2(slices) shuffle rounds
+            const unsigned votes = __ballot_sync(MC_FULL_MASK, blocked);
+            unsigned every = 1u;  // bit 0 of every group of pointLanes bits
+            for (int sft = pointLanes; sft < 32; sft <<= 1) every |= every << sft;
+            blocked = (votes & (every << pi)) != 0u;
+        }
         // C: order dependence inside the chunk, walking only the unblocked points in ascending order; lanes
         // 0..cnt-1 (slice 0) hold the points
         const bool holder = lane < cnt;  // slice 0 lanes: pi == lane
