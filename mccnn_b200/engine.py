@@ -455,10 +455,8 @@ class PeerGather:
 
 def gather_point_logits(local_logits, world_size, group=None):
     """Segmentation variant of the closing collective: per-point logits [N_r, F] with a
-    different N_r on every rank.  ONE all_gather: every rank contributes a block padded to the largest N_r whose first
-    row carries its live row count, so no separate size exchange is needed.  `max_rows` is agreed without a collective
-    when the caller shards a batch it knows completely; otherwise it is exchanged here (a second, 8-byte all_gather).
-    Returns [sum N_r, F] in rank order == the order of the unsharded packed batch."""
+    different N_r on every rank: an 8-byte all_gather of the row counts, then ONE all_gather of blocks padded to the
+    largest N_r.  Returns [sum N_r, F] in rank order == the order of the unsharded packed batch."""
     import torch.distributed as dist
     if world_size == 1:
         return local_logits
