@@ -24,6 +24,9 @@ def make_cloud(n, dist, rng):
             keep = rng.uniform(size=m) < np.sqrt(np.clip((p[:, 0] / L[0] + 0.5 - 0.2) / 0.6, 0.01, 1.0))
             out.append(p[keep])
         return np.concatenate(out)[:n].astype(np.float32)
+    if dist == "lattice":  # quantised coordinates (multiples of 1/8 in [-1, 1]): duplicates, points exactly on cell
+        # boundaries and pair distances exactly equal to common radii -- the float predicates' boundary cases
+        return (rng.integers(0, 17, (n, 3)).astype(np.float32) / np.float32(8.0) - np.float32(1.0)).astype(np.float32)
     raise ValueError(dist)
 
 

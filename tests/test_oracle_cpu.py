@@ -9,7 +9,7 @@ from oracle import cpu as O
 from oracle import numpy_ops as NP
 
 CASES = [(1, 512, "cube", False, 0.1), (3, 400, "sphere", True, 0.2), (2, 300, "cube", False, 0.45),
-         (2, 200, "sphere", False, 1.9)]
+         (2, 200, "sphere", False, 1.9), (2, 600, "lattice", True, 0.125)]
 
 
 def _grid(pts, bids, feats, B, r, sinv=True):

@@ -43,6 +43,8 @@ CASES = [
     (3, 700, "cube", True, 0.4, True),
     (2, 333, "sphere", False, 1.9, True),     # n = 1: whole cloud in one cell
     (2, 5000, "room", False, 0.25, False),    # absolute radius, batch-global box (ScanNet style)
+    (2, 2000, "lattice", True, 0.25, False),  # duplicates, points on cell boundaries, distances == r exactly
+    (3, 1500, "lattice", False, 0.125, True), # the same with per-cloud relative radius (extent 2 -> r = 0.25)
 ]
 
 
