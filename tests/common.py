@@ -145,3 +145,38 @@ def model_case(name):
     else:
         args = (cin, B, k, False)
     return inputs, args
+
+
+# ------------------------------------------------------------------------------------------------ data-set cases
+def make_dataset_models(num=10, seed=0):
+    """Synthetic in-memory models for the DataSet tests: (points f64 [n,3], normals f64 [n,3], features f64 [n,4]
+    = normal + one scalar, labels i32 [n,1], category)."""
+    models = []
+    for m in range(num):
+        rng = np.random.default_rng([seed, m])
+        n = int(rng.integers(300, 900))
+        v = rng.normal(size=(n, 3))
+        v /= np.linalg.norm(v, axis=1, keepdims=True)
+        pts = v * rng.uniform(0.3, 1.0, (1, 3))            # an ellipsoid: a distinct largest axis per model
+        feats = np.concatenate([v, rng.uniform(-1, 1, (n, 1))], axis=1)
+        labels = rng.integers(0, 5, (n, 1)).astype(np.int32)
+        models.append((pts, v.copy(), feats, labels, int(m % 4)))
+    return models
+
+
+DATASET_CASES = {
+    # every protocol, fixed number of points per model, rotation augmentation of points and of the normal features
+    "sampled": dict(ctor=dict(numPoints=256, ptDropOut=1.0, pointFeatures=True, pointLabels=False, pointNormals=True,
+                              useCategories=True, pointCategories=False, batchSize=4, allowedSamplings=[0, 1, 2, 3, 4],
+                              augment=True, augmentMainAxis=1, augmentSmallRotations=True, augmentedFeatures=[0],
+                              seed=7), epochs=2),
+    # all points of every model (one acceptance pass), point drop-out, labels, per-point categories, a point budget
+    "full": dict(ctor=dict(numPoints=0, ptDropOut=0.9, pointFeatures=False, pointLabels=True, pointNormals=True,
+                           useCategories=True, pointCategories=True, batchSize=5, allowedSamplings=[0, 1, 2, 3],
+                           maxPtsxBatch=2500, augment=True, augmentMainAxis=2, augmentSmallRotations=False, seed=11),
+                 epochs=1),
+    # more points than some models have (wrap-around passes), first-n selection
+    "wrap": dict(ctor=dict(numPoints=1000, ptDropOut=0.8, pointFeatures=True, pointLabels=True, pointNormals=True,
+                           useCategories=False, pointCategories=False, batchSize=3, allowedSamplings=[0, 1, 2, 3, 4],
+                           uniformSelectFirst=True, seed=3), epochs=1),
+}
