@@ -4,8 +4,10 @@
 In the reference this layer is TensorFlow (tf.layers.batch_normalization, tf.matmul, tf.nn.relu).  Here every function
 is one launch of mccnn_b200/csrc/dense.cu per layer: inference batch norms are folded into per-column (scale, shift)
 vectors -- cached until a variable changes -- and applied in the prologue / epilogue of the layer's FP32 GEMM.
-Inference mode only (moving mean / variance, epsilon 1e-3 as tf.layers.batch_normalization); training-mode statistics
-would mix rows across the capacity padding and are rejected.  Live row counts of capacity-padded inputs
+Inference (the measured path): moving mean / variance, epsilon 1e-3 as tf.layers.batch_normalization.  Training
+(isTraining=True, exact mode only): the same functions run as differentiable torch ops -- batch statistics with the
+moving averages updated at TensorFlow's momentum 0.99, dropout with keepProb -- so that, together with the autograd
+wiring of the Monte-Carlo ops (MCConvModule), loss.backward() reaches every variable of a network.  Live row counts of capacity-padded inputs
 (runtime.count_of) are honoured and propagated.
 """
 import torch
@@ -21,12 +23,43 @@ def _store(store):
     return store if store is not None else _vars.default_store()
 
 
+BN_MOMENTUM = 0.99  # tf.layers.batch_normalization default (moving = 0.99 * moving + 0.01 * batch)
+
+
+def _bn_vars(c, name, vs):
+    return (vs.get_variable(name + "/gamma", [c], "ones"), vs.get_variable(name + "/beta", [c], "zeros"),
+            vs.get_variable(name + "/moving_mean", [c], "zeros"), vs.get_variable(name + "/moving_variance", [c], "ones"))
+
+
+def _bn_train(x, name, vs):
+    """Training-mode batch norm as tf.layers.batch_normalization(training=True): normalise with the batch mean and
+    (biased) variance, update the moving statistics in place (the reference runs the UPDATE_OPS collection with every
+    step, ModelNet/ModelNet.py:199-203).  Plain differentiable torch ops; exact-shape tensors only."""
+    from . import runtime as _rtm
+    if _rtm.mode() == "planned" or _cnt(x) is not None:
+        raise RuntimeError("mccnn_b200: training-mode batch norm needs exact-shape tensors (not a planned run)")
+    x = _real(x)
+    gamma, beta, mean, var = _bn_vars(x.shape[1], name, vs)
+    bm = x.mean(dim=0)
+    bv = x.var(dim=0, unbiased=False)
+    with torch.no_grad():
+        mean.mul_(BN_MOMENTUM).add_(bm.detach(), alpha=1.0 - BN_MOMENTUM)
+        var.mul_(BN_MOMENTUM).add_(bv.detach(), alpha=1.0 - BN_MOMENTUM)
+    return (x - bm) * torch.rsqrt(bv + BN_EPSILON) * gamma + beta
+
+
+def _dropout(x, keepProb, use):
+    if not use or keepProb >= 1.0:
+        return x
+    return torch.nn.functional.dropout(x, p=1.0 - float(keepProb), training=True)  # scales by 1 / keepProb as tf.nn.dropout
+
+
 def _bn_affine(c, training, name, vs):
     """(scale, shift) of an inference batch norm: y = x * scale + shift.  Creates the four TF variables on first use
     (gamma 1, beta 0, moving_mean 0, moving_variance 1) and caches the folded vectors until one of them changes
     (tensor._version counts in-place updates)."""
     if training:
-        raise NotImplementedError("mccnn_b200 covers the forward/inference path; training-mode batch norm is not built")
+        raise RuntimeError("internal: the folded batch norm is the inference path")
     gamma = vs.get_variable(name + "/gamma", [c], "ones")
     beta = vs.get_variable(name + "/beta", [c], "zeros")
     mean = vs.get_variable(name + "/moving_mean", [c], "zeros")
@@ -123,8 +156,26 @@ def concat(values, axis=1):
 
 
 def batch_normalization(inputs, training, name, store=None):
+    if training:
+        return _bn_train(inputs, name, _store(store))
     scale, shift = _bn_affine(inputs.shape[1], training, name, _store(store))
     return _affine_act(inputs, scale, shift, False)
+
+
+def _mlp_train(x, vs, layerName, widths, bnNames, initBN, keepProb, useDropOut):
+    """MLP_1_hidden / MLP_2_hidden in training mode (utils/MCNetworkUtils.py:20-107): same variables, torch ops."""
+    if initBN is not None:
+        x = _bn_train(x, layerName + initBN, vs)
+    x = _real(x)
+    n = len(widths) - 1
+    for l in range(n):
+        w = vs.get_variable(layerName + '_weights%d' % (l + 1), [widths[l], widths[l + 1]], "glorot")
+        vs.add_to_collection('weight_decay_loss', w)
+        b = vs.get_variable(layerName + '_biases%d' % (l + 1), [widths[l + 1]], "zeros")
+        x = torch.addmm(b, x, w)
+        if l < n - 1:
+            x = _dropout(torch.relu(_bn_train(x, layerName + bnNames[l], vs)), keepProb, useDropOut)
+    return x
 
 
 def MLP_2_hidden(features, numInputFeatures, hidden1_units, hidden2_units, numOutFeatures, layerName, keepProb,
@@ -133,6 +184,9 @@ def MLP_2_hidden(features, numInputFeatures, hidden1_units, hidden2_units, numOu
     whole head: the initial batch norm is the prologue of layer 1, each hidden batch norm + ReLU the epilogue of
     its layer."""
     vs = _store(store)
+    if isTraining:
+        return _mlp_train(features, vs, layerName, [numInputFeatures, hidden1_units, hidden2_units, numOutFeatures],
+                          ["_BN_h1", "_BN_h2"], "_BN_Init" if useInitBN else None, keepProb, useDropOut)
     pre = _bn_affine(numInputFeatures, isTraining, layerName + "_BN_Init", vs) if useInitBN else None
     w1 = vs.get_variable(layerName + '_weights1', [numInputFeatures, hidden1_units], "glorot")
     vs.add_to_collection('weight_decay_loss', w1)
@@ -152,6 +206,9 @@ def MLP_1_hidden(features, numInputFeatures, hidden_units, numOutFeatures, layer
                  useDropOut=False, store=None):
     """utils/MCNetworkUtils.py:71-107."""
     vs = _store(store)
+    if isTraining:
+        return _mlp_train(features, vs, layerName, [numInputFeatures, hidden_units, numOutFeatures], ["_BN_h"], None,
+                          keepProb, useDropOut)
     w1 = vs.get_variable(layerName + '_weights1', [numInputFeatures, hidden_units], "glorot")
     vs.add_to_collection('weight_decay_loss', w1)
     b1 = vs.get_variable(layerName + '_biases1', [hidden_units], "zeros")
@@ -168,10 +225,15 @@ def conv_1x1(layerName, inputs, numInputs, numOutFeatures, store=None):
     w = vs.get_variable(layerName + '_weights', [numInputs, numOutFeatures], "glorot")
     vs.add_to_collection('weight_decay_loss', w)
     b = vs.get_variable(layerName + '_biases', [numOutFeatures], "zeros")
+    if torch.is_grad_enabled() and (w.requires_grad or b.requires_grad or
+                                    (isinstance(inputs, torch.Tensor) and inputs.requires_grad)):
+        return torch.addmm(b, _real(inputs), w)   # differentiable (training): plain torch, cuBLAS
     return _dense(inputs, w, b)
 
 
 def batch_norm_RELU_drop_out(layerName, inFeatures, isTraining, usedDropOut, keepProb, store=None):
     """utils/MCNetworkUtils.py:128-142 (dropout is the identity at inference)."""
+    if isTraining:
+        return _dropout(torch.relu(_bn_train(inFeatures, layerName + "_BN", _store(store))), keepProb, usedDropOut)
     scale, shift = _bn_affine(inFeatures.shape[1], isTraining, layerName + "_BN", _store(store))
     return _affine_act(inFeatures, scale, shift, True)

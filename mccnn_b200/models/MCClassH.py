@@ -11,8 +11,6 @@ from ._net import Net
 
 def create_network(points, batchIds, features, numInputFeatures, batchSize, k, numOutCat, isTraining, keepProbConv,
                    keepProbFull, useConvDropOut=False, useDropOutFull=True, store=None):
-    if isTraining:
-        raise NotImplementedError("mccnn_b200 covers the forward/inference path (no path drop-out)")
     rMax = math.sqrt(3.0) + 0.1
     ph = PointHierarchy(points, features, batchIds, [0.1, 0.4, rMax], "MCClassH_PH", batchSize)
     net = Net(ph, 0.25, isTraining, useConvDropOut, keepProbConv, store)
@@ -41,4 +39,11 @@ def create_network(points, batchIds, features, numInputFeatures, batchSize, k, n
     x = net.conv("Conv_2_2", ph.features_[1], numInputFeatures, 0.4, 1, out_features=2 * k)
     logits2 = upper(x, "_2")
 
-    return logits1 + logits2
+    if not isTraining:
+        return logits1 + logits2
+    # training: one path is dropped at random (models/MCClassH.py:193-209): p <= 0.66 keeps path 1, p >= 0.33 keeps
+    # path 2, the sum is rescaled by 2 / (number of kept paths)
+    import torch
+    p = float(torch.rand(1).item())
+    m1, m2 = float(p <= 0.66), float(p >= 0.33)
+    return (2.0 / (m1 + m2)) * (m1 * logits1 + m2 * logits2)
