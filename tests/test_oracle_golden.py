@@ -18,7 +18,7 @@ from common import make_conv_weights, rel_err, sum_err
 from oracle import cpu as O
 
 FILES = sorted(f for f in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
-               if not os.path.basename(f).startswith("model_"))  # model_*.npz: tests/test_models_*.py
+               if not os.path.basename(f).startswith(("model_", "dataset_")))  # those: tests/test_models_*.py, test_dataset_*.py
 
 
 def test_fixtures_present():
