@@ -579,7 +579,8 @@ def run_reference(args, rank, world, dev):
     h2d = sum(t.numel() * t.element_size() for t in pinned[0])
     return {"impl": "reference",
             "metric": "MC-conv fwd points/sec (MCClassS, 1024 pts, batch 32 per GPU)", "value": round(value, 1),
-            "unit": "points/s", "n_gpus": 1, "steps": steps, "warmup": warm, "ms_per_step": round(ms_per_step, 4),
+            "unit": "points/s", "n_gpus": 1, "launched_ranks": world, "steps": steps, "warmup": warm,
+            "ms_per_step": round(ms_per_step, 4),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic sphere-surface clouds (seeded), random-init weights",
             "config": {"workload": "MCClassS forward, %d clouds x %d points, k=%d, %d classes" % (B, P, k, NUM_CAT),
