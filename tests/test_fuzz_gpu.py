@@ -1,0 +1,78 @@
+"""Randomised parity sweep: 40 seeded configurations drawn over batch size, cloud size (ragged or not), point
+distribution, radius, relative / absolute radius, feature counts and convolution kind -- the whole op chain of one
+convolution (aabb -> sort -> Poisson samples -> neighbours -> pdf -> conv -> gradients) against the CPU oracle:
+indices bit-exact, pdf 1e-5 relative, conv / gradients 1e-5 of their sums' |terms|."""
+import numpy as np
+import pytest
+
+from common import make_batch, make_conv_weights, rel_err, sum_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _draw(seed):
+    rng = np.random.default_rng(1000 + seed)
+    dist = ["cube", "sphere", "room", "lattice"][int(rng.integers(0, 4))]
+    scaleInv = bool(rng.integers(0, 2)) if dist != "room" else False
+    B = int(rng.integers(1, 7))
+    N = int(rng.integers(40, 1500))
+    if scaleInv:
+        radius = float(rng.choice([0.05, 0.1, 0.17, 0.25, 0.4, 0.8, 1.9]))
+    else:
+        ext = 6.0 if dist == "room" else 2.0 if dist == "lattice" else 1.0
+        radius = float(ext * rng.choice([0.05, 0.1, 0.125, 0.3]))
+    combin = bool(rng.integers(0, 2))
+    C = int(rng.choice([1, 2, 3, 5])) if combin else int(rng.choice([8, 16, 24]))
+    Co = int(rng.integers(1, 12)) if combin else C
+    while combin and (-(-(C * Co) // 8) * 8) % C != 0:   # op constraint: 8 * nb multiple of C (spatial_conv.cc:290)
+        Co += 1
+    return dict(dist=dist, scaleInv=scaleInv, B=B, N=N, radius=radius, combin=combin, C=C, Co=Co,
+                ragged=bool(rng.integers(0, 2)), avg=bool(rng.integers(0, 2)),
+                window=float(rng.choice([0.2, 0.25])), seed=seed)
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_random_configuration(seed):
+    import torch
+    import mccnn_b200.MCConvModule as M
+    from oracle import cpu as O
+    c = _draw(seed)
+    dev = torch.device("cuda:0")
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    A = lambda t: t.detach().cpu().numpy()  # noqa: E731
+    B, r, si = c["B"], c["radius"], c["scaleInv"]
+    pts, bids, feats = make_batch(B, c["N"], c["dist"], seed=50 + seed, num_features=c["C"], ragged=c["ragged"])
+    w = make_conv_weights(c["C"], c["Co"], c["combin"], seed=seed)
+
+    def chain(X, conv):
+        mn, mx = X.compute_aabb(conv(pts), conv(bids), B, si)
+        keys, idx = X.sort_points_step1(conv(pts), conv(bids), mn, mx, B, r, si)
+        sp, sb, sf, cells = X.sort_points_step2(conv(pts), conv(bids), conv(feats), keys, idx, mn, mx, B, r, si)
+        smp, smpb, sidx = X.poisson_sampling(sp, sb, cells, mn, mx, r * 0.5, B, si)
+        start, pairs = X.find_neighbors(smp, smpb, sp, cells, mn, mx, r, B, si)
+        pdf = X.compute_pdf(sp, sb, mn, mx, start, pairs, c["window"], r, B, si)
+        out = X.spatial_conv(sp, sf, sb, pdf, smp, start, pairs, mn, mx, *[conv(a) for a in w], c["Co"], c["combin"], B,
+                             r, si, c["avg"])
+        return dict(mn=mn, mx=mx, keys=keys, idx=idx, sp=sp, sb=sb, sf=sf, cells=cells, smp=smp, smpb=smpb, sidx=sidx,
+                    start=start, pairs=pairs, pdf=pdf, out=out)
+
+    g = chain(M, T)
+    o = chain(O, lambda a: a)
+    for name in ("mn", "mx", "keys", "idx", "sp", "sb", "sf", "cells", "smp", "smpb", "sidx", "start", "pairs"):
+        assert np.array_equal(A(g[name]).reshape(-1), np.asarray(o[name]).reshape(-1)), (name, c)
+    if o["pairs"].shape[0] == 0:
+        return
+    assert rel_err(A(g["pdf"]), o["pdf"], 0.0) <= 1e-5, c
+    args = (o["sp"], o["sf"], o["sb"], o["pdf"], o["smp"], o["start"], o["pairs"], o["mn"], o["mx"])
+    scale = O.spatial_conv(*args, *w, c["Co"], c["combin"], B, r, si, c["avg"], abs_sum=True)
+    assert sum_err(A(g["out"]), o["out"], scale) <= 1e-5, c
+    # gradients on the same geometry
+    G = np.random.default_rng(seed).uniform(-1, 1, o["out"].shape).astype(np.float32)
+    w_op = (w[0], w[3], w[1], w[4], w[2], w[5])
+    attrs = (c["Co"], c["combin"], B, r, si, c["avg"])
+    want = O.spatial_conv_grad(*args, *w_op, G, *attrs)
+    gscale = O.spatial_conv_grad(*args, *w_op, G, *attrs, abs_sum=True)
+    got = M.spatial_conv_grad(*[T(a) for a in args], *[T(a) for a in w_op], T(G), *attrs)
+    for k, (a, b, s) in enumerate(zip(got, want, gscale)):
+        err = np.abs(A(a).astype(np.float64) - b) / (np.maximum(s, np.abs(b).mean()) + 1e-30)
+        assert err.max() <= 1e-5, (k, c)
