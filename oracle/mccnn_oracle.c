@@ -325,7 +325,8 @@ void orc_get_sampled_features(int M, int C, const int *idx, const float *feats, 
  *     atomics); 1: double accumulation (the order-free value both sides must approach); 2: the sum of the
  *     ABSOLUTE contributions per output (the scale against which a float32 sum's error is measured: outputs are
  *     signed sums that cancel, so an error relative to the result itself is unbounded for any summation order,
- *     the reference's included).
+ *     the reference's included).  The scale also propagates magnitudes through the MLP, because a kernel value
+ *     is itself a cancelling sum of O(1) products.
  * ---------------------------------------------------------------------------------------------- */
 void orc_spatial_conv(int avg, int scaleInv, int K, int C, int Co, int M, int combin, float radius,
                       const float *pts, const int *bids, const float *feats, const float *pdfs,
@@ -361,6 +362,23 @@ void orc_spatial_conv(int avg, int scaleInv, int K, int C, int Co, int M, int co
                 a += b2[nr];
                 h2[t] = a > 0.0f ? a : 0.0f;
             }
+            /* accumDouble == 2 (error scale): magnitudes propagated through the three layers -- the sum of |terms| a
+             * forward error analysis of the kernel value is relative to.  (|kappa| itself would hide the
+             * cancellation INSIDE the small MLP: a kernel value near zero is a difference of O(1) products.) */
+            double m1[ORC_BLOCK_MLP], m2[ORC_BLOCK_MLP];
+            if (accumDouble == 2) {
+                for (int t = 0; t < ORC_BLOCK_MLP; ++t) {
+                    int nr = q * ORC_BLOCK_MLP + t;
+                    m1[t] = fabs((double)d[0] * W1[nr * 3]) + fabs((double)d[1] * W1[nr * 3 + 1]) +
+                            fabs((double)d[2] * W1[nr * 3 + 2]) + fabs((double)b1[nr]);
+                }
+                for (int t = 0; t < ORC_BLOCK_MLP; ++t) {
+                    int nr = q * ORC_BLOCK_MLP + t;
+                    double a = fabs((double)b2[nr]);
+                    for (int u = 0; u < ORC_BLOCK_MLP; ++u) a += m1[u] * fabs((double)W2[nr * ORC_BLOCK_MLP + u]);
+                    m2[t] = a;
+                }
+            }
             for (int t = 0; t < ORC_BLOCK_MLP; ++t) {
                 int nr = q * ORC_BLOCK_MLP + t;
                 if (nr >= nOut) continue;
@@ -370,7 +388,13 @@ void orc_spatial_conv(int avg, int scaleInv, int K, int C, int Co, int M, int co
                 int c = nr % C;
                 int o = combin ? nr / C : c;
                 float contrib = (feats[(size_t)j * C + c] * a) / w;
-                acc[(size_t)i * outC + o] += accumDouble == 2 ? fabs((double)contrib) : (double)contrib;
+                if (accumDouble == 2) {
+                    double mk = fabs((double)bo[nr]);
+                    for (int u = 0; u < ORC_BLOCK_MLP; ++u) mk += m2[u] * fabs((double)Wo[nr * ORC_BLOCK_MLP + u]);
+                    acc[(size_t)i * outC + o] += fabs((double)feats[(size_t)j * C + c]) * mk / fabs((double)w);
+                } else {
+                    acc[(size_t)i * outC + o] += (double)contrib;
+                }
                 accf[(size_t)i * outC + o] += contrib;
             }
         }
