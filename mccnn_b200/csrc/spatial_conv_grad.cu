@@ -25,12 +25,13 @@ namespace {
 
 constexpr int kGradWarps = 4;
 constexpr int kGradPairsPerCta = 1024;
+constexpr int kGradRadiusTable = 1024;  // per-cloud radius kept in shared memory up to this batch size
 constexpr int kGradVals = 22;  // per neuron: dW1[3], db1, dW2[8], db2, dWo[8], dbo
 
 struct GradArgs {
     bool avg, scaleInv, combin;
     float radius;
-    int K, M, C, outC, nOut, numBlocks;
+    int K, M, B, C, outC, nOut, numBlocks;
     const float* pts;
     const int* bids;
     const float* feats;
@@ -46,7 +47,7 @@ struct GradArgs {
     float* dFeat;
 };
 
-__global__ void __launch_bounds__(kGradWarps * 32) spatial_conv_grad_kernel(const GradArgs a) {
+__global__ void __launch_bounds__(kGradWarps * 32, 4) spatial_conv_grad_kernel(const GradArgs a) {
     __shared__ float sAcc[kGradWarps][8][kGradVals];
     const int lane = lane_id(), warp = threadIdx.x >> 5;
     const int t = lane & 7, grp = lane >> 3, gbase = lane & 24;
@@ -72,25 +73,79 @@ __global__ void __launch_bounds__(kGradWarps * 32) spatial_conv_grad_kernel(cons
 #pragma unroll
     for (int u = 0; u < 8; ++u) aW2[u] = aWo[u] = 0.f;
 
+    // per-cloud radius in shared memory: removes the batch id -> box -> radius chain from every pair
+    __shared__ float sRad[kGradRadiusTable];
+    const bool radiusTable = a.B <= kGradRadiusTable;
+    if (radiusTable) {
+        for (int bb = threadIdx.x; bb < a.B; bb += blockDim.x)
+            sRad[bb] = a.scaleInv ? a.radius * max_extent(a.mn, a.mx, bb) : a.radius;
+        __syncthreads();
+    }
+
     const int p0 = blockIdx.x * kGradPairsPerCta;
     const int p1 = min(a.K, p0 + kGradPairsPerCta);
-    for (int base = p0 + warp * 4; base < p1; base += kGradWarps * 4) {  // warp-uniform trip count
+    // two-stage software pipeline over the warp's steps: (A) pair + pdf of step s+2, (B) everything addressed through
+    // the pair (coordinates, batch id, neighbour range, feature, incoming gradient) of step s+1, compute step s --
+    // the dependent global loads of a step are in flight while the two previous steps are computed
+    struct StageA {
+        int2 pr;
+        float pdf;
+        bool live;
+    };
+    struct StageB {
+        float px, py, pz, sx, sy, sz, pdf, f, g;
+        int b, lo, hi, j;
+        bool live;
+    };
+    auto load_a = [&](int base) {
+        StageA A;
         const int p = base + grp;
-        const bool live = p < p1;
-        int2 pr = live ? a.pairs[p] : make_int2(0, 0);
-        const int j = pr.x, i = pr.y;
-        const float pdf = live ? a.pdfs[p] : 1.0f;
-        const int b = a.bids[j];
-        const float r = a.scaleInv ? a.radius * max_extent(a.mn, a.mx, b) : a.radius;
-        const float dx = (a.pts[(size_t)j * 3] - a.samples[(size_t)i * 3]) / r;
-        const float dy = (a.pts[(size_t)j * 3 + 1] - a.samples[(size_t)i * 3 + 1]) / r;
-        const float dz = (a.pts[(size_t)j * 3 + 2] - a.samples[(size_t)i * 3 + 2]) / r;
-        const int lo = a.start[i];
-        const int hi = (i < a.M - 1) ? a.start[i + 1] : a.K;
-        const float w = live ? pdf * (a.avg ? (float)(hi - lo) : 1.0f) : 1.0f;  // dead slots contribute exact zeros
+        A.live = p < p1;
+        A.pr = A.live ? a.pairs[p] : make_int2(0, 0);
+        A.pdf = A.live ? a.pdfs[p] : 1.0f;
+        return A;
+    };
+    auto load_b = [&](const StageA& A) {
+        StageB Bv;
+        const int j = A.pr.x, i = A.pr.y;
+        Bv.j = j;
+        Bv.live = A.live;
+        Bv.pdf = A.pdf;
+        Bv.px = a.pts[(size_t)j * 3];
+        Bv.py = a.pts[(size_t)j * 3 + 1];
+        Bv.pz = a.pts[(size_t)j * 3 + 2];
+        Bv.sx = a.samples[(size_t)i * 3];
+        Bv.sy = a.samples[(size_t)i * 3 + 1];
+        Bv.sz = a.samples[(size_t)i * 3 + 2];
+        Bv.b = a.bids[j];
+        Bv.lo = a.start[i];
+        Bv.hi = (i < a.M - 1) ? a.start[i + 1] : a.K;
+        const bool use = A.live && neuronLive;
+        Bv.f = use ? a.feats[(size_t)j * a.C + c] : 0.0f;
+        Bv.g = use ? a.outGrad[(size_t)i * a.outC + o] : 0.0f;
+        return Bv;
+    };
+    const int step = kGradWarps * 4;
+    const int base0 = p0 + warp * 4;
+    StageA nextA = load_a(base0);
+    StageB nextB = load_b(nextA);
+    nextA = load_a(base0 + step);
+    for (int base = base0; base < p1; base += step) {  // warp-uniform trip count
+        const StageB cur = nextB;
+        if (base + step < p1) {
+            nextB = load_b(nextA);
+            nextA = load_a(base + 2 * step);
+        }
+        const bool live = cur.live;
+        const int j = cur.j;
+        const float r = radiusTable ? sRad[cur.b]
+                                    : (a.scaleInv ? a.radius * max_extent(a.mn, a.mx, cur.b) : a.radius);
+        const float dx = (cur.px - cur.sx) / r;
+        const float dy = (cur.py - cur.sy) / r;
+        const float dz = (cur.pz - cur.sz) / r;
+        const float w = live ? cur.pdf * (a.avg ? (float)(cur.hi - cur.lo) : 1.0f) : 1.0f;  // dead slots: exact zeros
         const bool use = live && neuronLive;
-        const float f = use ? a.feats[(size_t)j * a.C + c] : 0.0f;
-        const float g = use ? a.outGrad[(size_t)i * a.outC + o] : 0.0f;
+        const float f = cur.f, g = cur.g;
 
         // forward, recomputed
         const float z1 = fmaf(dx, w1x, fmaf(dy, w1y, fmaf(dz, w1z, b1v)));
@@ -257,6 +312,7 @@ extern "C" int mc_spatial_conv_grad(int avg, int scaleInv, int numNeighbors, int
         a.radius = radius;
         a.K = numNeighbors;
         a.M = numSamples;
+        a.B = batchSize;
         a.C = C;
         a.outC = combin ? numOutFeatures : C;
         a.nOut = nOut;
