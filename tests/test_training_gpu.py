@@ -53,6 +53,7 @@ def test_mcclasss_learns_a_toy_problem():
             assert all(bool(torch.isfinite(v.grad).all()) for v in trainable)
         opt.step()
         losses.append(float(loss.detach()))
+    print("loss first5 %.4f last5 %.4f" % (np.mean(losses[:5]), np.mean(losses[-5:])))
     assert np.mean(losses[-5:]) < 0.6 * np.mean(losses[:5]), losses
     # held-out clouds, still normalised with batch statistics (30 steps at momentum 0.99 move the running averages
     # only a quarter of the way, so the inference path is checked for consistency below, not for accuracy)
@@ -61,6 +62,7 @@ def test_mcclasss_learns_a_toy_problem():
         for s in range(4):
             batch = _toy_batch(B, n, 900 + s, dev)
             correct += int((net(batch, True).argmax(dim=1) == batch[3]).sum())
+    print("held-out correct %d / 32" % correct)
     assert correct >= 24, correct                             # >= 75 % of 32 held-out clouds
     # the moving statistics were updated, and the inference path (folded BN, own dense kernels) consumes them
     mm = store.vars["Reduce_1_In_BN_BN/moving_mean"]
