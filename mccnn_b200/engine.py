@@ -14,8 +14,12 @@ The graph reads its three inputs from ONE contiguous static block and leaves log
 result block, so a host-resident batch costs exactly one H2D copy, one graph launch and one D2H copy
 (`HostForward`).  `PipelinedForward` / `PipelinedHostForward` keep several such forwards in flight on one GPU.
 
-`shard_batch` / `gather_logits` implement the multi-GPU partition of BASELINE.json's north_star: independent clouds
-of a packed batch are split contiguously over the ranks and ONE all_gather of the per-cloud logits closes the step.
+`shard_batch` + `PeerGather` implement the multi-GPU partition of BASELINE.json's north_star: independent clouds of a
+packed batch are split contiguously over the ranks and ONE all-gather of the per-cloud logits closes the step --
+`PeerGather` does it with one own kernel over NVLink peer memory (csrc/peer_gather.cu) that is captured into the
+forward's graph as an `epilogue`; `gather_logits` is the NCCL equivalent (fallback, unequal shards, CPU/gloo tests).
+`global_box` and `gather_point_logits` serve the segmentation networks (batch-global bounding box for absolute radii,
+per-point logits of unequal length).
 """
 import torch
 
