@@ -169,3 +169,53 @@ def test_empty_inputs():
     assert start.shape == (0, 1) and pairs.shape == (0, 2)
     qp, qb, qi = O.poisson_sampling(e3, e1, cells, mn, mx, 0.4, 1, True)
     assert qi.shape == (0,)
+
+
+# ---- hypothesis: small adversarial clouds (duplicates, flat / collinear sets, tiny and huge extents, any radius) -----
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+_coord = st.one_of(st.floats(-2.0, 2.0, width=32), st.sampled_from([0.0, 0.5, -0.5, 0.25, 1.0]))
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.lists(st.tuples(_coord, _coord, _coord), min_size=2, max_size=40),
+       st.sampled_from([0.05, 0.1, 0.25, 0.5, 1.0, 1.9]), st.booleans())
+def test_oracle_invariants_on_arbitrary_small_clouds(points, r, scale_inv):
+    pts = np.asarray(points, np.float32)
+    if float((pts.max(0) - pts.min(0)).max()) < 1e-3:      # degenerate box: cell size 0 (undefined in the reference too)
+        return
+    N = pts.shape[0]
+    bids = np.zeros((N, 1), np.int32)
+    feats = np.arange(N, dtype=np.float32).reshape(N, 1)
+    mn, mx, keys, idx, sp, sb, sf, cells = _grid(pts, bids, feats, 1, r, scale_inv)
+    n = cells.shape[1]
+    if n ** 3 > 200000:
+        return
+    # sort: a stable permutation by key, cell table = run boundaries
+    assert np.array_equal(np.sort(idx), np.arange(N))
+    skeys = np.empty_like(keys)
+    skeys[idx] = keys
+    assert np.all(np.diff(skeys) >= 0)
+    order = np.argsort(idx)
+    assert np.all(np.diff(order)[skeys[1:] == skeys[:-1]] > 0)
+    assert np.array_equal(sf[:, 0], order.astype(np.float32))
+    flat = cells.reshape(-1, 2)
+    assert int((flat[:, 1] - flat[:, 0]).sum()) == N
+    # neighbours (samples == points): exact brute force with the reference's float expression
+    start, pairs = O.find_neighbors(sp, sb, sp, cells, mn, mx, r, 1, scale_inv)
+    ext = np.float32((mx - mn).max())
+    rb = np.float32(r) * ext if scale_inv else np.float32(r)
+    d = (sp[None, :, :] - sp[:, None, :]).astype(np.float32)        # d[i, j] = p_j - p_i
+    t = (d[..., 1] * d[..., 1]).astype(np.float32)
+    t = (d[..., 0].astype(np.float64) * d[..., 0] + t).astype(np.float32)
+    t = (d[..., 2].astype(np.float64) * d[..., 2] + t).astype(np.float32)
+    inside = np.sqrt(t, dtype=np.float32) < rb
+    want = {(int(j), int(i)) for i, j in zip(*np.nonzero(inside))}
+    assert set(map(tuple, pairs.tolist())) == want
+    # Poisson disk: accepted points pairwise not within r, every point within r of an accepted one (same predicate)
+    qp, qb, qi = O.poisson_sampling(sp, sb, cells, mn, mx, r, 1, scale_inv)
+    acc = np.zeros(N, bool)
+    acc[qi] = True
+    sub = inside[np.ix_(qi, qi)]
+    assert not (sub & ~np.eye(len(qi), dtype=bool)).any()
+    assert inside[:, acc].any(axis=1).all()
