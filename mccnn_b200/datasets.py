@@ -89,3 +89,57 @@ class ShapeNetDataSet(DataSet):
         data = np.loadtxt(modelPath + ".txt", usecols=range(7), ndmin=2)
         pts, normals = data[:, 0:3], data[:, 3:6]
         return pts, normals, normals if self.useNormalsAsFeatures_ else None, data[:, 6:7]
+
+
+class ScanNetDataSet(DataSet):
+    """ScanNet rooms prepared by the reference's ScanNet/genScanNetData.py: `<dataFolder>/<room>_{pos,labels,colors}.npy`
+    plus rooms.txt / num_points.txt / scannet_{train,val,test}.txt / labels.txt / weights.txt
+    (ScanNet/ScanNetDataSet.py:33-135).  Rooms are centred on load; all points are used, a batch holds at most
+    maxNumPtsxBatch points, nothing is cached (maxNumPtsCache = 0, as in the reference)."""
+
+    def __init__(self, dataset, batchSize, ptDropOut, maxNumPtsxBatch=600000, augment=False, useColorsAsFeatures=False,
+                 dataFolder="data_mccnn", seed=None, device="cuda"):
+        if 0 < maxNumPtsxBatch < 600000:
+            raise RuntimeError('The number of points per batch should be big enough to store'
+                               ' all the models (greater than 600000).')
+        self.useColorsAsFeatures_ = useColorsAsFeatures
+        self.dataFolder_ = dataFolder
+        super().__init__(0, ptDropOut, useColorsAsFeatures, True, False, False, False, batchSize, [0], 0,
+                         maxNumPtsxBatch, augment, 2, False, False, [], [], seed, device=device)
+        rooms = np.loadtxt(dataFolder + "/rooms.txt", dtype='str')
+        numPoints = np.loadtxt(dataFolder + "/num_points.txt") * ptDropOut
+        split = ["scannet_train.txt", "scannet_val.txt", "scannet_test.txt"][dataset if dataset in (0, 1) else 2]
+        wanted = set(np.atleast_1d(np.loadtxt(dataFolder + "/" + split, dtype='str')))
+        idx = np.array([i for i in range(len(rooms)) if rooms[i] in wanted], dtype=np.int64)
+        self.fileList_ = rooms[idx]
+        self.numPts_ = numPoints[idx]
+        self.semLabels_ = np.loadtxt(dataFolder + "/labels.txt", dtype='str', delimiter=':')
+        weights = np.loadtxt(dataFolder + "/weights.txt")
+        self.weights_ = 1.0 / np.log(1.2 + weights[0][: len(self.semLabels_)])
+        self.weights_[0] = 0.0
+
+    def get_labels(self):
+        return self.semLabels_
+
+    def get_weights(self, labels):
+        """Per-point loss weights of the labels [n,1] (ScanNet/ScanNetDataSet.py:104-118); tensors stay on their device."""
+        import torch
+        if len(self.weights_) == 0:
+            raise RuntimeError('No weights associated to the labels.')
+        if isinstance(labels, torch.Tensor):
+            w = torch.as_tensor(self.weights_, dtype=torch.float32, device=labels.device)
+            return w[labels.reshape(-1).long()].reshape(-1, 1)
+        return np.asarray(self.weights_)[np.asarray(labels).reshape(-1)].reshape(-1, 1)
+
+    def get_accuracy_masks(self, labels):
+        """1 for annotated points (label != 0), 0 otherwise (ScanNet/ScanNetDataSet.py:120-133)."""
+        import torch
+        if isinstance(labels, torch.Tensor):
+            return (labels.reshape(-1, 1) != 0).to(torch.float32)
+        return (np.asarray(labels).reshape(-1, 1) != 0).astype(np.float64)
+
+    def _load_model_from_disk_(self, modelPath):
+        pts = np.load(self.dataFolder_ + "/" + modelPath + "_pos.npy")
+        labels = np.load(self.dataFolder_ + "/" + modelPath + "_labels.npy")
+        features = np.load(self.dataFolder_ + "/" + modelPath + "_colors.npy") if self.useColorsAsFeatures_ else None
+        return pts - np.mean(pts, axis=0), None, features, labels.reshape((-1, 1))

@@ -118,3 +118,41 @@ def test_shapenet_dataset_equals_the_reference(tmp_path, monkeypatch):
     assert ours.get_categories() == [tuple(c) for c in theirs.get_categories()]
     assert ours.get_categories_seg_parts() == theirs.get_categories_seg_parts()
     _same(_batches(ours), _batches(theirs))
+
+
+def _write_scannet(root, rng):
+    rooms = ["scene%04d_00" % i for i in range(8)]
+    npts = []
+    for r in rooms:
+        n = int(rng.integers(400, 900))
+        npts.append(n)
+        np.save(os.path.join(root, r + "_pos.npy"), rng.uniform(-3, 3, (n, 3)))
+        np.save(os.path.join(root, r + "_labels.npy"), rng.integers(0, 4, (n,)).astype(np.int32))
+        np.save(os.path.join(root, r + "_colors.npy"), rng.uniform(0, 1, (n, 3)))
+    np.savetxt(os.path.join(root, "rooms.txt"), np.array(rooms), fmt="%s")
+    np.savetxt(os.path.join(root, "num_points.txt"), np.array(npts, np.float64))
+    for split, sel in (("train", rooms[:4]), ("val", rooms[4:6]), ("test", rooms[6:])):
+        np.savetxt(os.path.join(root, "scannet_%s.txt" % split), np.array(sel), fmt="%s")
+    with open(os.path.join(root, "labels.txt"), "w") as f:
+        f.write("0:unannotated\n1:wall\n2:floor\n3:chair\n")
+    np.savetxt(os.path.join(root, "weights.txt"), rng.uniform(0.01, 0.5, (2, 4)))
+
+
+@pytest.mark.parametrize("colors", [False, True])
+def test_scannet_dataset_equals_the_reference(tmp_path, colors):
+    Ref = _reference("ScanNet", "ScanNetDataSet")
+    from mccnn_b200.datasets import ScanNetDataSet
+    root = str(tmp_path)
+    _write_scannet(root, np.random.default_rng(2))
+    kw = dict(dataset=0, batchSize=3, ptDropOut=0.8, maxNumPtsxBatch=0, augment=True, useColorsAsFeatures=colors,
+              dataFolder=root, seed=4)
+    ours, theirs = ScanNetDataSet(device="cpu", **kw), Ref(**kw)
+    assert list(ours.fileList_) == list(theirs.fileList_) and np.array_equal(ours.numPts_, theirs.numPts_)
+    np.testing.assert_allclose(ours.weights_, theirs.weights_)
+    ob, tb = _batches(ours), _batches(theirs)
+    _same(ob, tb)
+    labels = ob[0][4]
+    np.testing.assert_allclose(ours.get_weights(labels).numpy(), theirs.get_weights(tb[0][4]), atol=1e-7)
+    assert np.array_equal(ours.get_accuracy_masks(labels).numpy(), theirs.get_accuracy_masks(tb[0][4]))
+    with pytest.raises(RuntimeError):
+        ScanNetDataSet(0, 1, 1.0, maxNumPtsxBatch=1000, dataFolder=root, device="cpu")
