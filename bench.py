@@ -1,26 +1,30 @@
 #!/usr/bin/env python
-"""bench.py -- MCClassS forward points/s on synthetic 32 x 1024-point clouds (BASELINE.json metric, configs[1]).
+"""bench.py -- Monte-Carlo-convolution forward points/s on the BASELINE.json configurations.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 1..5] [--scaling weak|strong]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A step = one MCClassS forward (models/MCClassS.py topology: 3-level Poisson hierarchy, 3 Monte-Carlo convolutions,
-dense glue, 40 logits per cloud) over one packed batch of 32 clouds x 1024 points per GPU.  Multi-GPU: independent
-clouds sharded over the ranks (32 clouds per GPU, weak scaling), ONE NCCL all_gather of the per-cloud logits per step.
+Default = the configuration the metric is quoted on, `configs[1]`: MCClassS forward (models/MCClassS.py: 3-level
+Poisson hierarchy, 3 Monte-Carlo convolutions, dense glue, 40 logits per cloud) over packed batches of 32 clouds x 1024
+points.  A step = one forward over one batch.  Multi-GPU: independent clouds sharded over the ranks, ONE all-gather of
+the logits per step; the headline line is weak scaling (32 clouds per GPU) and carries a `scaling_strong` block with
+the strong split of ONE batch of 32 (32/N clouds per GPU).  `--config 3|4|5` run MCClassH 32x4096 /
+MCSeg 16x8192 / MCSegScanNet 8x80000 (strong split at N > 1: the configurations are quoted "sharded 8 GPUs"),
+`--config 1` the single spatial_conv op; the default N = 1 line carries them as `other_configs`.
 
 One JSON line on rank 0:
-  value   points/s, whole job, batches already resident in HBM, CUDA-graph replay, CUDA-event timed per step
-          (L2 flushed between steps, outside the timed intervals), max over ranks;
-  e2e     the same metric through the host-facing call (pinned host buffers -> H2D -> forward -> D2H logits),
-          wall clock around every call;
-  roofline   dominant kernel of the step: algorithmic bytes / its mean CUDA-event duration,
-             against the measured HBM copy bandwidth in MEASURED_PEAKS.json;
-  cpu_baseline  the oracle port of the same forward on the host (1 thread) + NumPy spatial_conv of config 1;
+  value      points/s, whole job, batches already resident in HBM, CUDA-graph replay, `--pipeline` forwards in flight,
+             one CUDA-event pair around exactly K steps, max over ranks;
+  latency    one forward at a time, L2 flushed before each, CUDA events per step;
+  e2e        the same metric through the host-facing call (pinned host block -> H2D -> forward -> D2H logits);
+  roofline   dominant kernel: algorithmic bytes / its CUDA-event duration vs the measured HBM peak;
+  cpu_baseline  the oracle port of the same forward on the host + NumPy spatial_conv of config 1 (N = 1 only).
 `--impl reference` runs the reference's own CUDA kernels (oracle/_ref, built from /root/reference/tf_ops/*.cu) through
-the same op sequence with the reference's host choreography (oracle/ref_pipeline.py) -- the reference has no CPU
-implementation of this path; its GPU path re-compiled for sm_100a IS the reference arm.
+the reference's op sequence and host choreography (oracle/ref_nets.py) -- the reference has no CPU implementation of this
+path; its GPU path re-compiled for sm_100a IS the reference arm.  That arm imports nothing of mccnn_b200.
 """
 import argparse
+import importlib
 import json
 import math
 import os
@@ -36,16 +40,68 @@ os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-from common import make_batch, make_conv_weights  # noqa: E402
+from synthetic import make_batch, make_conv_weights, named_variable  # noqa: E402
 
-NUM_CAT = 40
-RADII = [0.1, 0.4, math.sqrt(3.0) + 0.1]
-CONV_RADII = [0.2, 0.8, math.sqrt(3.0) + 0.1]
+# ----------------------------------------------------------------------------------------------- workloads
+# BASELINE.json `configs`, 1-based.  Sizes and distributions: SURVEY.md section 8(d).
+WORKLOADS = {
+    1: dict(kind="op", title="single spatial_conv op", B=1, P=1024, dist="sphere", cin=3, cout=8, radius=0.1),
+    2: dict(kind="net", model="MCClassS", B=32, P=1024, dist="sphere", cin=1, k=64, classes=40),
+    3: dict(kind="net", model="MCClassH", B=32, P=4096, dist="sphere", cin=1, k=64, classes=40),
+    4: dict(kind="net", model="MCSeg", B=16, P=8192, dist="sphere", cin=1, k=64, cats=16, parts=50),
+    5: dict(kind="net", model="MCSegScanNet", B=8, P=80000, dist="room", cin=1, k=32, sem=21),
+}
+
+
+def workload_string(w, clouds):
+    """The same string in both arms (the driver compares `config.workload`)."""
+    if w["kind"] == "op":
+        return ("single spatial_conv op (tf_ops/spatial_conv.cu), %d cloud x %d points, %d -> %d features, radius %g, "
+                "neighbour list and pdfs given" % (clouds, w["P"], w["cin"], w["cout"], w["radius"]))
+    tail = {"MCClassS": "%d classes" % w.get("classes", 0), "MCClassH": "%d classes" % w.get("classes", 0),
+            "MCSeg": "%d categories, %d parts" % (w.get("cats", 0), w.get("parts", 0)),
+            "MCSegScanNet": "%d semantic classes, absolute radii" % w.get("sem", 0)}[w["model"]]
+    return "%s forward (models/%s.py), %d clouds x %d points per GPU, k=%d, %s, %d input feature" % (
+        w["model"], w["model"], clouds, w["P"], w["k"], tail, w["cin"])
+
+
+def metric_string(w):
+    if w["kind"] == "op":
+        return "spatial_conv fwd points/sec (1 cloud x %d pts, %d->%d features)" % (w["P"], w["cin"], w["cout"])
+    if w["model"] == "MCClassS":
+        return "MC-conv fwd points/sec (MCClassS, 1024 pts, batch 32 per GPU)"
+    return "MC-conv fwd points/sec (%s, %d pts, batch %d)" % (w["model"], w["P"], w["B"])
+
+
+def net_args(w, clouds, arm):
+    """Positional arguments after (points, batchIds, features[, catLabels]): ours = the reference's create_network
+    signature (isTraining False, keep probabilities 1), reference arm = oracle/ref_nets.py's inference signature."""
+    m = w["model"]
+    if m in ("MCClassS", "MCClassH"):
+        a = (w["cin"], clouds, w["k"], w["classes"])
+    elif m == "MCSeg":
+        a = (w["cin"], w["cats"], w["parts"], clouds, w["k"])
+    else:
+        a = (w["cin"], w["sem"], clouds, w["k"])
+    return a + ((False, 1.0, 1.0) if arm == "ours" else ())
+
+
+def out_cols(w):
+    return {"MCClassS": w.get("classes"), "MCClassH": w.get("classes"), "MCSeg": w.get("parts"),
+            "MCSegScanNet": w.get("sem")}[w["model"]]
+
+
+def per_cloud_output(w):
+    return w["model"] in ("MCClassS", "MCClassH")
+
+
+def host_batch(w, clouds, seed):
+    pts, bids, feats = make_batch(clouds, w["P"], w["dist"], seed=seed, num_features=w["cin"])
+    return pts, bids, feats
 
 
 # ----------------------------------------------------------------------------------------------- utilities
@@ -67,6 +123,7 @@ class ClockSampler:
             self.thread.start()
         except Exception:
             self.proc = None
+        return self
 
     def _read(self):
         for line in self.proc.stdout:
@@ -98,462 +155,543 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def measured_peak_gbs():
+def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+            d = json.load(f)
+        return float(d["hbm_gbs"]), float(d["bf16_tflops"]), "measured (MEASURED_PEAKS.json)"
     except Exception:
-        return 6650.0, "fallback (B200_PROFILING.md)"
+        return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
 
 
-def algorithmic_bytes(op, call, sizes, B, k, n_in=1):
-    """SURVEY.md section 8(d) per-op byte counts for call number `call` of `op` inside one MCClassS forward."""
-    N = [sizes["N0"], sizes["M1"], sizes["M2"], sizes["M3"]]
-    K = [sizes["K1"], sizes["K2"], sizes["K3"]]
-    hier_n = [max(1, int(np.float32(1.0) / np.float32(r))) for r in RADII]
-    conv_n = [max(1, int(np.float32(1.0) / np.float32(r))) for r in CONV_RADII]
-    feat_c = [n_in, n_in, n_in]                      # features carried through the hierarchy
-    conv_c = [n_in, 2 * k, 4 * k]
-    conv_co = [k, 2 * k, 4 * k]
-    if op == "compute_aabb":
-        return 16 * N[0] + 24 * B
-    if op == "sort_points":                          # calls: hier L0, hier L1, hier L2, conv1, conv2, conv3
-        order = [("h", 0), ("h", 1), ("h", 2), ("c", 0), ("c", 1), ("c", 2)][call]
-        lvl = order[1]
-        n = hier_n[lvl] if order[0] == "h" else conv_n[lvl]
-        return N[lvl] * 48 + 20 * B * n ** 3        # geometry only (C = 0): features move in sort_features
-    if op == "sort_features":                        # calls: conv1, conv2, conv3
-        return N[call] * (8 * conv_c[call] + 4)
-    if op == "poisson_sampling":
-        return 13 * N[call] + 8 * B * hier_n[call] ** 3 + 20 * N[call + 1]
-    if op == "get_sampled_features":
-        return N[call + 1] * (4 + 8 * feat_c[call])
-    if op == "transform_indexs":
-        return 8 * N[call] + 8 * N[call + 1]
-    if op == "dense_layer":                          # Reduce_1, Reduce_2
-        rows, kin, nout = [(N[1], k, 2 * k), (N[2], 2 * k, 4 * k)][call]
-        return 4 * (rows * kin + kin * nout + rows * nout + 2 * kin + 3 * nout)
-    if op == "mlp_rows":                             # the three layers of the head in one launch
-        w = [4 * k, 2 * k, k, NUM_CAT]
-        return 4 * (B * w[0] + B * w[3] + sum(a * b + 3 * b for a, b in zip(w[:-1], w[1:])) + 2 * w[0])
-    if op in ("find_neighbors_count", "find_neighbors_pack", "find_neighbors", "find_neighbors_fused"):
-        M, Np, G = N[call + 1], N[call], B * conv_n[call] ** 3
-        full = 16 * M + 12 * Np + 8 * min(G, 27 * M) + 4 * M + 8 * K[call]
-        return full if op != "find_neighbors_count" else full - 8 * K[call]
-    if op == "compute_pdf":
-        return 12 * K[call] + 4 * N[call + 1] + 12 * N[call]
-    if op == "spatial_conv":
-        C, Co = conv_c[call], conv_co[call]
-        nOut = C * Co if call == 0 else C
-        nb = (nOut + 7) // 8
-        return (12 * K[call] + 4 * C * K[call] + 12 * N[call] + 12 * N[call + 1] + 4 * N[call + 1] +
-                4 * Co * N[call + 1] + 4 * (8 * nb * 13 + nOut * 9))
-    return 0
+def ncu_profile_numbers():
+    try:
+        with open(os.path.join(ROOT, "profiles", "top_kernel_traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
 
 
 def flush_l2(buf):
     buf.add_(1.0)  # read + write a buffer larger than the 126 MB L2
 
 
-# ----------------------------------------------------------------------------------------------- our arm
-def run_ours(args, rank, world, dev):
+def max_over_ranks(x, world, dev):
+    if world == 1:
+        return float(x)
     import torch.distributed as dist
-    import mccnn_b200
-    from mccnn_b200 import ops, variables
+    t = torch.tensor([x], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def barrier(world):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+
+
+# ----------------------------------------------------------------------------------------------- our arm
+def named_store(dev):
+    """Variables drawn by synthetic.named_variable (seeded by NAME): the reference arm draws the same values without
+    importing this package."""
+    from mccnn_b200 import variables
+
+    class NamedStore(variables.VariableStore):
+        def get_variable(self, name, shape, initializer="glorot"):
+            if name not in self.vars:
+                self.vars[name] = torch.from_numpy(named_variable(name, shape)).to(self.device)
+            return variables.VariableStore.get_variable(self, name, shape, initializer)
+
+    return NamedStore(device=dev)
+
+
+def measure_ours(w, args, rank, world, dev, clouds, split, steps, warmup, depth, detail=True):
+    """One network workload on this rank's shard.  split: "weak" (every rank its own batches of `clouds` clouds) or
+    "strong" (ONE global batch of w["B"] clouds, this rank takes its contiguous share).  Returns a dict of measurements
+    (times already reduced to the max over ranks)."""
+    import torch.distributed as dist
+    from mccnn_b200 import runtime
     from mccnn_b200._lib import lib
-    from mccnn_b200.engine import (PlannedForward, PipelinedForward, HostForward, PipelinedHostForward,
-                                   gather_logits, pack_batch)
-    from mccnn_b200.models import MCClassS
+    from mccnn_b200.engine import (PlannedForward, PipelinedForward, HostForward, PipelinedHostForward, PeerGather,
+                                   gather_logits, gather_point_logits, pack_batch, shard_batch)
+    from mccnn_b200.profiling import OpProfile
 
-    B, P, k = args.batch, args.points, args.k
-    store = variables.VariableStore(device=dev, seed=0)
+    model = importlib.import_module("mccnn_b200.models." + w["model"])
+    store = named_store(dev)
+    sharded = world > 1 and split == "strong"
+    total_clouds = w["B"] if sharded else clouds * world
+    n_batches = 4 if w["B"] * w["P"] <= 1 << 17 else 2
 
-    def fn(p, b, f):
-        return MCClassS.create_network(p, b, f, 1, B, k, NUM_CAT, False, 1.0, 1.0, store=store)
+    def make(i):
+        if sharded:  # every rank draws the same global batch and keeps its contiguous share of the clouds
+            g = host_batch(w, w["B"], seed=7000 + i)
+            p, b, f, _, _ = shard_batch(*g, w["B"], rank, world)
+            return np.ascontiguousarray(p), np.ascontiguousarray(b), np.ascontiguousarray(f)
+        return host_batch(w, clouds, seed=1000 * rank + i)
 
-    n_batches = 4
-    host = [make_batch(B, P, "sphere", seed=1000 * rank + i) for i in range(n_batches)]
+    host = [make(i) for i in range(n_batches)]
     pinned = [tuple(torch.from_numpy(a).pin_memory() for a in h) for h in host]
     resident = [tuple(t.to(dev) for t in h) for h in pinned]
+    n_local = host[0][0].shape[0]
+    cat = None
+    if w["model"] == "MCSeg":  # one object category per cloud, constant over the batches (clouds are equally sized)
+        cat = torch.from_numpy((host[0][1] % w["cats"]).astype(np.int32)).to(dev)
+    absolute = w["model"] == "MCSegScanNet"
 
-    eng = PlannedForward(fn, B, use_graph=True, slack=1.3)
+    def fn(p, b, f):
+        lead = (p, b, f) + ((cat,) if cat is not None else ())
+        if sharded and absolute:  # batch-global box across the shards (one 6-float all-reduce inside the forward)
+            with runtime.sharded():
+                return model.create_network(*lead, *net_args(w, clouds, "ours"), store=store)
+        return model.create_network(*lead, *net_args(w, clouds, "ours"), store=store)
+
+    rows = clouds if per_cloud_output(w) else n_local
+    cols = out_cols(w)
+    points_per_step = total_clouds * w["P"]
+
+    # ---- the step's closing collective: per-cloud logits -> an epilogue captured into each lane's graph (own kernel
+    # over NVLink peer memory, NCCL as fallback); per-point logits of unequal length -> issued behind each forward
+    gather_mode = "none"
+    after = None
+
+    def epilogues(n):
+        nonlocal gather_mode, after
+        if world == 1:
+            return None
+        if not per_cloud_output(w):
+            gather_mode = "NCCL all_gather of padded per-point logits (count prefix) issued behind each forward"
+            after = lambda out, flag: gather_point_logits(out, world)  # noqa: E731
+            return None
+        if os.environ.get("MCCNN_GATHER", "peer") == "peer":
+            try:
+                eps = [PeerGather(rows, cols, dev) for _ in range(n)]
+                gather_mode = ("all_gather of the per-cloud logits as ONE own kernel over NVLink peer memory "
+                               "(symmetric buffers, peer stores + flags; csrc/peer_gather.cu), a node of each "
+                               "lane's CUDA graph")
+                return eps
+            except Exception as exc:  # noqa: BLE001
+                sys.stderr.write("bench: peer-memory all_gather unavailable (%r); using NCCL\n" % (exc,))
+        groups = [dist.new_group(list(range(world))) for _ in range(n)]
+        gather_mode = "NCCL all_gather captured in each lane's CUDA graph (one communicator per lane)"
+        return [(lambda o, g=g: gather_logits(o, total_clouds, world, group=g)) for g in groups]
+
+    if sharded and absolute:
+        depth = 1  # the box all-reduce inside the forward uses the default communicator: one forward in flight
+    eps = epilogues(depth + 1)
+    eng = PlannedForward(fn, rows, use_graph=True, slack=1.3, epilogue=None if eps is None else eps[depth])
     eng.calibrate(resident)
-    sizes = dict(zip(["M1", "M2", "M3", "K1", "K2", "K3"], eng.plan.sizes))
-    sizes["N0"] = B * P
     flush = torch.zeros(192 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # 192 MiB > L2
-
-    def step(i):
-        out, flag = eng.run_async(*resident[i % n_batches])
-        if world > 1:
-            out = gather_logits(out, B * world, world)
-        return out, flag
-
-    for i in range(max(args.warmup, 3)):
-        step(i)
+    warm = max(warmup, 3)
+    for i in range(warm):
+        eng.run_async(*resident[i % n_batches])
     torch.cuda.synchronize(dev)
 
-    # ---- value: device-resident inputs, per-step CUDA events, L2 flushed between steps
-    sampler = ClockSampler(dev.index)
-    sampler.start()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize(dev)
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    # ---- latency: one forward at a time, per-step CUDA events, L2 flushed between steps
+    barrier(world)
+    lat_steps = steps if detail else min(steps, 10)
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(lat_steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(lat_steps)]
     flags = torch.zeros((1,), dtype=torch.int32, device=dev)
-    launches0 = lib.mc_launch_count()
-    t_wall0 = time.perf_counter()
-    for i in range(args.steps):
+    for i in range(lat_steps):
         flush_l2(flush)
         starts[i].record()
-        out, flag = step(i)
+        out, flag = eng.run_async(*resident[i % n_batches])
+        if after is not None:
+            after(out, flag)
         ends[i].record()
         flags += flag
     torch.cuda.synchronize(dev)
-    t_wall = time.perf_counter() - t_wall0
-    if world > 1:
-        dist.barrier()
-    per_step = [s.elapsed_time(e) for s, e in zip(starts, ends)]
-    ms_local = float(np.mean(per_step))
+    barrier(world)
+    latency_ms = max_over_ranks(float(np.mean([s.elapsed_time(e) for s, e in zip(starts, ends)])), world, dev)
     overflowed = int(flags.item())
-    t = torch.tensor([ms_local], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    latency_ms = float(t.item())          # one forward at a time (L2 flushed before each)
-    serial_value = B * P * world / (latency_ms * 1e-3)
+    res = {"latency_ms": latency_ms, "points_per_step": points_per_step, "gather_mode": gather_mode, "depth": depth,
+           "sizes": list(eng.plan.sizes), "clouds_per_gpu": clouds, "local_points": n_local}
 
-    # ---- value: throughput with `depth` forwards in flight (independent CUDA graphs on `depth` streams).  The timed
-    # region rotates over enough distinct resident batches that their inputs exceed the L2 (no flush possible inside
-    # an overlapped region); one event pair around exactly K steps.
-    depth = max(1, args.pipeline)
-    n_pipe = max(n_batches, int(math.ceil(140e6 / (B * P * 20.0))))     # 20 B of input per point -> > 126 MB L2
-    # resident batches in the single-block layout the captured graphs read (points | batch ids | features)
+    # ---- value: `depth` forwards in flight (independent CUDA graphs on `depth` streams); the timed region rotates
+    # over distinct resident batches; one event pair around exactly K steps
+    in_bytes = sum(t.numel() * t.element_size() for t in resident[0])
+    n_pipe = n_batches
+    if detail and in_bytes * n_batches < 140e6 and in_bytes < 4e6:
+        n_pipe = max(n_batches, int(math.ceil(140e6 / in_bytes)))   # inputs of the rotation exceed the 126 MB L2
     pipe_res = [pack_batch(*r) for r in resident]
     for i in range(n_batches, n_pipe):
-        pipe_res.append(pack_batch(*(torch.from_numpy(a).to(dev)
-                                     for a in make_batch(B, P, "sphere", seed=1000 * rank + i))))
-    # multi-GPU: the step's single collective (all_gather of the per-cloud logits) is captured INTO each lane's CUDA
-    # graph (one NCCL communicator per lane: lanes run concurrently), so a step stays one graph launch on the host.
-    # Fallback if the capture is refused: the collective is issued on the lane's stream right behind the replay.
-    gather_mode, after = "none", None
-    pipe = None
-    if world > 1 and os.environ.get("MCCNN_BENCH_DIAG_NO_GATHER") == "1":
-        gather_mode = "DIAGNOSTIC: collective skipped in the pipelined loops (not a valid bench line)"
-        pipe = PipelinedForward(fn, B, depth=depth, slack=1.3)
-        pipe.calibrate(resident)
-    elif world > 1:
-        # (1) own kernel over NVLink peer memory (csrc/peer_gather.cu), captured into each lane's graph;
-        # (2) NCCL all_gather captured into each lane's graph (one communicator per lane); (3) NCCL per step
-        want = os.environ.get("MCCNN_GATHER", "peer")
-        if want == "peer":
-            try:
-                from mccnn_b200.engine import PeerGather
-                gathers = [PeerGather(B, NUM_CAT, dev) for _ in range(depth)]
-                pipe = PipelinedForward(fn, B, depth=depth, slack=1.3, epilogues=gathers)
-                pipe.calibrate(resident)
-                gather_mode = ("all_gather as ONE own kernel over NVLink peer memory (symmetric buffers, peer stores + "
-                               "flags; csrc/peer_gather.cu), a node of each lane's CUDA graph")
-            except Exception as exc:  # noqa: BLE001
-                sys.stderr.write("bench: peer-memory all_gather unavailable (%r); trying NCCL in the graph\n" % (exc,))
-                pipe = None
-        if pipe is None and want in ("peer", "nccl_graph"):
-            try:
-                groups = [dist.new_group(list(range(world))) for _ in range(depth)]
-                pipe = PipelinedForward(fn, B, depth=depth, slack=1.3, epilogues=[
-                    (lambda o, g=g: gather_logits(o, B * world, world, group=g)) for g in groups])
-                pipe.calibrate(resident)
-                gather_mode = "NCCL all_gather captured in each lane's CUDA graph (one communicator per lane)"
-            except Exception as exc:  # noqa: BLE001
-                sys.stderr.write("bench: graph-captured all_gather unavailable (%r); issuing it per step\n" % (exc,))
-                pipe = None
-    if pipe is None:
-        pipe = PipelinedForward(fn, B, depth=depth, slack=1.3)
-        pipe.calibrate(resident)
-        if world > 1 and not gather_mode.startswith("DIAG"):
-            gather_mode = "all_gather issued on the lane's stream behind each graph replay"
-            after = lambda out, flag: gather_logits(out, B * world, world)  # noqa: E731
-    pflags = torch.zeros((1,), dtype=torch.int32, device=dev)
-
-    def pstep(i):
-        return pipe.submit_packed(pipe_res[i % n_pipe], after=after)
-
-    for i in range(max(args.warmup, 3) * depth):
-        pstep(i)
+        pipe_res.append(pack_batch(*(torch.from_numpy(a).to(dev) for a in make(i))))
+    pipe = PipelinedForward(fn, rows, depth=depth, slack=1.3, epilogues=None if eps is None else eps[:depth])
+    pipe.calibrate(resident)
+    for i in range(warm * depth):
+        pipe.submit_packed(pipe_res[i % n_pipe], after=after)
     pipe.join()
     torch.cuda.synchronize(dev)
-    if world > 1:
-        dist.barrier()
+    barrier(world)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     tw0 = time.perf_counter()
     ev0.record()
-    for i in range(args.steps):
-        pstep(i)
+    for i in range(steps):
+        pipe.submit_packed(pipe_res[i % n_pipe], after=after)
     pipe.join()
     ev1.record()
     torch.cuda.synchronize(dev)
-    t_wall_pipe = time.perf_counter() - tw0
-    if world > 1:
-        dist.barrier()
+    res["wall_s_timed_region"] = time.perf_counter() - tw0
+    barrier(world)
+    pflags = torch.zeros((1,), dtype=torch.int32, device=dev)
     for e in pipe.engines:
         pflags += e.plan.overflow
     overflowed += int(pflags.item())
-    t = torch.tensor([ev0.elapsed_time(ev1) / args.steps], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_per_step = float(t.item())
-    value = B * P * world / (ms_per_step * 1e-3)
+    res["ms_per_step"] = max_over_ranks(ev0.elapsed_time(ev1) / steps, world, dev)
+    res["value"] = points_per_step / (res["ms_per_step"] * 1e-3)
+    res["l2"] = ("timed region rotates over %d distinct resident batches (%.0f MB of inputs%s); the one-at-a-time "
+                 "latency run flushes L2 (192 MiB write) before every step" %
+                 (n_pipe, n_pipe * in_bytes / 1e6, " > 126 MB L2" if n_pipe * in_bytes > 126e6 else
+                  "; the forward's own intermediates exceed the L2" if w["B"] * w["P"] > 1 << 17 else ""))
+    res["plan_overflows"] = overflowed
 
-    # ---- kernels per forward (ours) + per-op CUDA-event timing in eager planned mode (every op visible)
-    eager = PlannedForward(fn, B, use_graph=False, slack=1.3, multistream=False)  # one stream: ops run back to back
+    # ---- kernels per forward + per-op CUDA-event timing in eager planned mode (every op visible, one stream)
+    eager = PlannedForward(fn, rows, use_graph=False, slack=1.3, multistream=False,
+                           epilogue=None)
     eager.plan, eager._shape_key = eng.plan, eng._shape_key
     eager.run_async(*resident[0])
     torch.cuda.synchronize(dev)
     c0 = lib.mc_launch_count()
     eager.run_async(*resident[0])
-    launches_per_forward = int(lib.mc_launch_count() - c0)
-    names = ["compute_aabb", "build_grid", "sort_points_step1", "sort_points_step2", "sort_features",
-             "transform_indexs", "find_neighbors_count", "find_neighbors_pack", "find_neighbors_fused", "compute_pdf",
-             "poisson_sampling", "get_sampled_features", "spatial_conv", "dense_layer", "mlp_rows", "scale_shift_act"]
-    orig = {n: getattr(ops, n) for n in names}
-    events = []
-
-    def wrap(n):
-        def w(*a, **kw):
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
-            r = orig[n](*a, **kw)
-            e.record()
-            events.append((n, s, e))
-            return r
-        return w
-
-    for n in names:
-        setattr(ops, n, wrap(n))
-    op_iters = min(args.steps, 10)
+    res["launches_per_forward"] = int(lib.mc_launch_count() - c0) + int("own kernel" in gather_mode)
+    op_iters = min(steps, 10) if detail else 3
+    tables = []
     for i in range(op_iters):
         flush_l2(flush)
-        # keep the GPU busy (~6 ms) while the host enqueues the whole forward, so that every event pair brackets
-        # kernel execution only and not the Python / allocator time between launches
-        torch.cuda._sleep(12_000_000)
-        eager.run_async(*resident[i % n_batches])
-        torch.cuda.synchronize(dev)
-    for n in names:
-        setattr(ops, n, orig[n])
-    per_call = {}
-    counters = {}
-    for idx, (n, s, e) in enumerate(events):
-        c = counters.get((n, idx // (len(events) // op_iters)), 0)
-        counters[(n, idx // (len(events) // op_iters))] = c + 1
-        per_call.setdefault((n, c), []).append(s.elapsed_time(e) * 1e3)
+        # keep the GPU busy while the host enqueues the whole forward, so that every event pair brackets kernel
+        # execution only and not the Python / allocator time between launches
+        torch.cuda._sleep(12_000_000 if w["B"] * w["P"] <= 1 << 17 else 40_000_000)
+        with OpProfile(clouds) as prof:
+            eager.run_async(*resident[i % n_batches])
+        tables.append(prof.table())
     kernels = []
-    for (n, c), v in per_call.items():
-        opname = "sort_points" if n == "build_grid" else n
-        by = algorithmic_bytes(opname, c, sizes, B, k)
-        us = float(np.median(v))  # median over the timed forwards: robust against a one-off host hiccup
-        kernels.append({"op": n, "call": c, "us": round(us, 2), "us_max": round(float(np.max(v)), 2),
-                        "alg_bytes": int(by), "gbs": round(by / us * 1e-3, 2) if us > 0 else None})
-    kernels.sort(key=lambda d: -d["us"])
-    peak, peak_src = measured_peak_gbs()
-    top = kernels[0]
-    traffic = None
-    prof = os.path.join(ROOT, "profiles", "top_kernel_traffic.json")
-    if os.path.exists(prof):
-        try:
-            with open(prof) as f:
-                traffic = json.load(f).get(top["op"] + ":" + str(top["call"]))
-        except Exception:
-            traffic = None
-    ncu = {}
-    if os.path.exists(prof):
-        try:
-            with open(prof) as f:
-                ncu = json.load(f)
-        except Exception:
-            ncu = {}
-    # spatial_conv against the tensor roofline (north_star: "tensor-pipe % of peak (spatial_conv)")
-    conv = max((kk for kk in kernels if kk["op"] == "spatial_conv"), key=lambda kk: kk["us"], default=None)
-    roofline_tensor = None
-    if conv is not None:
-        c = conv["call"]
-        Kc = [sizes["K1"], sizes["K2"], sizes["K3"]][c]
-        n_out = [k, 2 * k, 4 * k][c]                      # neurons: Cin*Co = k for Conv_1, C for the depth-wise ones
-        nb = (n_out + 7) // 8
-        flops = Kc * (176 * nb + 18 * n_out)
-        try:
-            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-                tpeak = float(json.load(f)["bf16_tflops"])
-            tsrc = "measured dense bf16 (MEASURED_PEAKS.json); the kernel computes fp32 via 3xTF32 mma.sync"
-        except Exception:
-            tpeak, tsrc = 2250.0, "nominal dense bf16"
-        ach = flops / (conv["us"] * 1e-6) / 1e12
-        roofline_tensor = {"bound": "tensor", "kernel": "spatial_conv (call %d of the forward)" % c,
-                           "achieved": round(ach, 3), "peak": tpeak, "peak_source": tsrc, "unit": "TFLOP/s",
-                           "frac": round(ach / tpeak, 5), "alg_flops_per_launch": int(flops),
-                           "us_per_launch": conv["us"],
-                           "tensor_pipe_active_pct_ncu": ncu.get("tensor_pipe_active_pct", {}).get(
-                               "spatial_conv:%d" % c),
-                           "note": "algorithmic FLOPs K*(176*nb + 18*Nout); 3xTF32 issues 3 MMAs per product and "
-                                   "the Monte-Carlo sum adds 4 membership MMAs per tile, so the pipe-active % "
-                                   "(ncu) is the utilisation figure, the TFLOP/s the useful-work figure"}
-    roofline = {"bound": "hbm", "kernel": "%s (call %d of the forward)" % (top["op"], top["call"]),
-                "achieved": top["gbs"], "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                "frac": round(top["gbs"] / peak, 5) if top["gbs"] else None, "traffic": traffic,
-                "alg_bytes_per_launch": top["alg_bytes"], "us_per_launch": top["us"],
-                "note": "whole step is latency-bound: working set ~10 MB << L2; per-op table in 'kernels'"}
+    for j, row in enumerate(tables[0]):
+        us = [t[j]["us"] for t in tables if j < len(t) and t[j]["op"] == row["op"]]
+        med = float(np.median(us))   # median over the timed forwards: robust against a one-off host hiccup
+        kernels.append({"op": row["op"], "call": row["call"], "us": round(med, 2), "us_max": round(float(np.max(us)), 2),
+                        "alg_bytes": row["alg_bytes"], "gbs": round(row["alg_bytes"] / med * 1e-3, 2) if med > 0 else None})
+    res["kernels"] = sorted(kernels, key=lambda d: -d["us"])
+    by_op = {}
+    for kr in kernels:
+        d = by_op.setdefault(kr["op"], {"calls": 0, "us": 0.0, "alg_bytes": 0})
+        d["calls"] += 1
+        d["us"] += kr["us"]
+        d["alg_bytes"] += kr["alg_bytes"]
+    res["by_op"] = by_op
 
-    # ---- e2e: host buffers, H2D + forward + D2H inside the timed call
-    # (a) one call at a time (latency), (b) `depth` calls in flight (throughput) -- every step copies its inputs from
-    # pinned host memory and its logits + overflow flag back, and every result is read on the host
-    pinned_blocks = [pack_batch(*h, pin=True) for h in pinned]   # the data loader's pinned staging buffers
+    # ---- e2e: host buffers, H2D + forward + D2H inside the timed call; every result is read on the host
+    pinned_blocks = [pack_batch(*h, pin=True) for h in pinned]
     hf = HostForward(eng, dev)
     for i in range(3):
         hf.call_packed(pinned_blocks[i % n_batches])
     torch.cuda.synchronize(dev)
+    barrier(world)
+    e2e_steps = steps if detail else min(steps, 10)
     t0 = time.perf_counter()
-    for i in range(args.steps):
-        res = hf.call_packed(pinned_blocks[i % n_batches])
-    e2e_latency_s = (time.perf_counter() - t0) / args.steps
+    for i in range(e2e_steps):
+        hf.call_packed(pinned_blocks[i % n_batches])
+    res["e2e_latency_s"] = max_over_ranks((time.perf_counter() - t0) / e2e_steps, world, dev)
     phf = PipelinedHostForward(pipe, dev)
-    checksum = 0.0
+    after_h = (lambda out: after(out, None)) if after is not None else None   # the host gets ALL logits
     for rep in range(2):
-        warm = [phf.submit_packed(pinned_blocks[i % n_batches]) for i in range(depth)]
-        for tk in warm:
+        warm_t = [phf.submit_packed(pinned_blocks[i % n_batches], after=after_h) for i in range(depth)]
+        for tk in warm_t:
             phf.result(tk)
-    if world > 1:
-        dist.barrier()
+    barrier(world)
     torch.cuda.synchronize(dev)
-    after_h = (lambda out: gather_logits(out, B * world, world)) if after is not None else None  # host gets ALL logits
+    checksum = 0.0
     t0 = time.perf_counter()
     tickets = []
-    for i in range(args.steps):
-        tk = phf.submit_packed(pinned_blocks[i % n_batches], after=after_h)
-        tickets.append(tk)
+    for i in range(steps):
+        tickets.append(phf.submit_packed(pinned_blocks[i % n_batches], after=after_h))
         if len(tickets) >= depth:                  # consume the oldest result before its lane is submitted to again
-            res = phf.result(tickets.pop(0))
-            checksum += float(res[0, 0])
+            checksum += float(phf.result(tickets.pop(0))[0, 0])
     while tickets:
-        res = phf.result(tickets.pop(0))
-        checksum += float(res[0, 0])
+        checksum += float(phf.result(tickets.pop(0))[0, 0])
     torch.cuda.synchronize(dev)
-    e2e_s = (time.perf_counter() - t0) / args.steps
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
-    h2d, d2h = hf.bytes_per_call(*pinned[0], B, NUM_CAT)
-    if world > 1:  # whole job: every rank copies its batch in and its result block + the gathered logits out
-        h2d, d2h = h2d * world, (B * world * NUM_CAT * 4 + 4 + (d2h if after is not None else 0)) * world
-    clocks = sampler.stop()  # sampled across the value, per-op and e2e regions
-
-    line = None
-    if rank == 0:
-        cpu = cpu_baseline(store, host[0], B, k) if world == 1 else None  # reported at N = 1 only
-        line = {
-            "metric": "MC-conv fwd points/sec (MCClassS, 1024 pts, batch 32 per GPU)", "value": round(value, 1),
-            "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": round(ms_per_step, 5), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic sphere-surface clouds (seeded), random-init weights",
-            "config": {"workload": "MCClassS forward (models/MCClassS.py), %d clouds x %d points per GPU, k=%d, "
-                                   "%d classes, 1 input feature" % (B, P, k, NUM_CAT),
-                       "parallelism": "dp%d (clouds sharded, one all_gather of logits)" % world,
-                       "collective": gather_mode,
-                       "concurrency": "%d forwards in flight per GPU (independent CUDA graphs on %d streams, "
-                                      "CUDA_DEVICE_MAX_CONNECTIONS=%s); every step is a complete forward of its own "
-                                      "batch" % (depth, depth, os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS")),
-                       "l2": "timed region rotates over %d distinct resident batches (%.0f MB of inputs > 126 MB L2); "
-                             "the one-at-a-time latency run flushes L2 (192 MiB write) before every step"
-                             % (n_pipe, n_pipe * B * P * 20.0 / 1e6),
-                       "levels": [sizes["N0"], sizes["M1"], sizes["M2"], sizes["M3"]],
-                       "pairs": [sizes["K1"], sizes["K2"], sizes["K3"]]},
-            "clocks": clocks,
-            "latency": {"ms_per_forward": round(latency_ms, 5), "points_per_s_one_at_a_time": round(serial_value, 1),
-                        "note": "one forward at a time, L2 flushed before each, CUDA events per step"},
-            "e2e": {"value": round(B * P * world / e2e_s, 1), "unit": "points/s", "ms_per_step": round(e2e_s * 1e3, 5),
-                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "one_at_a_time": {"value": round(B * P * world / e2e_latency_s, 1),
-                                      "ms_per_step": round(e2e_latency_s * 1e3, 5)},
-                    "note": "%d host calls in flight; each copies its batch from pinned host memory, runs the forward "
-                            "and returns logits + overflow flag to the host, every result is read on the host" % depth},
-            "gpu_launches": (launches_per_forward + int("peer memory" in gather_mode)) * args.steps,
-            "gpu_launches_per_step": launches_per_forward + int("peer memory" in gather_mode),
-            "wall_s_timed_region": round(t_wall_pipe, 4),
-            "plan_overflows": overflowed,
-            "roofline": roofline,
-            "roofline_tensor": roofline_tensor,
-            "kernels": kernels[:12],
-            "cpu_baseline": cpu,
-        }
-    return line
+    res["e2e_s"] = max_over_ranks((time.perf_counter() - t0) / steps, world, dev)
+    res["checksum"] = checksum
+    res["h2d"] = sum(t.numel() * t.element_size() for t in pinned[0]) * world
+    out_rows_total = phf.pipe.engines[0]._out_view.shape[0]
+    res["d2h"] = (out_rows_total * cols * 4 + 4) * world
+    if after is not None:  # every rank also reads the gathered per-point logits
+        res["d2h"] += int(max_over_ranks(n_local, world, dev)) * world * cols * 4 * world
+    res["store"] = store
+    res["host0"] = host[0]
+    return res
 
 
-def cpu_baseline(store, host_batch, B, k):
-    """Oracle port (oracle/mccnn_oracle.c + NumPy glue) of the same forward on the host, single thread, repeated for
-    >= ~10 s; plus the NumPy re-execution of config 1's spatial_conv that BASELINE.json names."""
-    from oracle import pipeline as OP, cpu as O, numpy_ops as NP
-    params = {n: v.detach().cpu().numpy() for n, v in store.vars.items()}
-    pts, bids, feats = host_batch
+def rooflines(res, w, k):
+    peak, tpeak, src = measured_peaks()
+    ncu = ncu_profile_numbers()
+    top = res["kernels"][0]
+    roof = {"bound": "hbm", "kernel": "%s (call %d of the forward)" % (top["op"], top["call"]),
+            "achieved": top["gbs"], "peak": peak, "peak_source": src, "unit": "GB/s",
+            "frac": round(top["gbs"] / peak, 5) if top["gbs"] else None,
+            "traffic": ncu.get(w.get("model", "op") + ":" + top["op"] + ":" + str(top["call"])),
+            "alg_bytes_per_launch": top["alg_bytes"], "us_per_launch": top["us"]}
+    alg = sum(kr["alg_bytes"] for kr in res["kernels"])
+    roof["whole_step"] = {"alg_bytes": int(alg), "gbs_at_latency": round(alg / (res["latency_ms"] * 1e-3) / 1e9, 1),
+                          "frac": round(alg / (res["latency_ms"] * 1e-3) / 1e9 / peak, 4)}
+    conv = max((kr for kr in res["kernels"] if kr["op"] == "spatial_conv"), key=lambda kr: kr["us"], default=None)
+    tens = None
+    if conv is not None:
+        tens = {"bound": "tensor", "kernel": "spatial_conv (call %d of the forward)" % conv["call"], "peak": tpeak,
+                "peak_source": src + "; dense bf16 -- the kernel computes fp32 via 3xTF32 mma.sync",
+                "unit": "TFLOP/s", "us_per_launch": conv["us"],
+                "tensor_pipe_active_pct_ncu": ncu.get("tensor_pipe_active_pct", {}).get(
+                    w.get("model", "op") + ":spatial_conv:%d" % conv["call"])}
+    return roof, tens
+
+
+def cpu_baseline_line(w, store, host_batch_, clouds):
+    """Oracle port of the same forward on the host cores: the C oracle ops (single thread) + torch CPU dense glue
+    through the restated reference topology (oracle/ref_nets.py), on a bounded sample of the workload; plus the NumPy
+    re-execution of config 1's spatial_conv that BASELINE.json names."""
+    from oracle import ref_nets, cpu as O, numpy_ops as NP
+    sample_clouds = clouds if w["B"] * w["P"] <= 1 << 15 else 1
+    pts, bids, feats = host_batch(w, sample_clouds, seed=1)
+    inputs = {"points": torch.from_numpy(pts), "batchIds": torch.from_numpy(bids), "features": torch.from_numpy(feats)}
+    if w["model"] == "MCSeg":
+        inputs["catLabels"] = torch.from_numpy((bids % w["cats"]).astype(np.int32))
+    params = {n: v.detach().cpu() for n, v in store.vars.items()}
     t0 = time.perf_counter()
     reps = 0
     while True:
-        OP.mcclasss_forward(pts, bids, feats, 1, B, k, NUM_CAT, params)
+        ref_nets.forward(w["model"], ref_nets.CpuOps(), params, named_variable, inputs,
+                         net_args(w, sample_clouds, "reference"))
         reps += 1
         el = time.perf_counter() - t0
         if el > 10.0 or reps >= 20:
             break
     fwd_s = el / reps
+    line = {"value": round(pts.shape[0] / fwd_s, 1), "unit": "points/s", "cores": 1, "kind": "port",
+            "sample": "%d of the %d clouds x %d points of a batch, %d repetitions, %.2f s per forward; single-threaded "
+                      "C oracle ops + torch CPU dense glue (%d threads)" % (sample_clouds, clouds, w["P"], reps, fwd_s,
+                                                                           torch.get_num_threads()),
+            "host_cores_available": os.cpu_count()}
     # config 1: single spatial_conv, 1 cloud x 1024 points, 3 -> 8 features, r = 0.1
-    p1, b1, f1 = make_batch(1, 1024, "sphere", seed=0, num_features=3)
-    mn, mx = O.compute_aabb(p1, b1, 1, True)
-    keys, idx = O.sort_points_step1(p1, b1, mn, mx, 1, 0.1, True)
-    sp, sb, sf, cells = O.sort_points_step2(p1, b1, f1, keys, idx, mn, mx, 1, 0.1, True)
-    start, pairs = O.find_neighbors(sp, sb, sp, cells, mn, mx, 0.1, 1, True)
-    pdf = O.compute_pdf(sp, sb, mn, mx, start, pairs, 0.2, 0.1, 1, True)
-    w = make_conv_weights(3, 8, True, seed=0)
+    w1 = WORKLOADS[1]
+    sp, sf, sb, pdf, start, pairs, mn, mx, wts = config1_inputs(w1, O)
     best = 1e9
     for _ in range(10):
         t1 = time.perf_counter()
-        NP.spatial_conv(sp, sf, sb, pdf, sp, start, pairs, mn, mx, *w, 8, True, 1, 0.1, True, True)
+        NP.spatial_conv(sp, sf, sb, pdf, sp, start, pairs, mn, mx, *wts, w1["cout"], True, 1, w1["radius"], True, True)
         best = min(best, time.perf_counter() - t1)
-    return {"value": round(pts.shape[0] / fwd_s, 1), "unit": "points/s", "cores": 1, "kind": "port",
-            "sample": "full workload batch (%d clouds x %d points), %d repetitions, %.2f s per forward, "
-                      "single-threaded C oracle + NumPy dense glue" % (B, pts.shape[0] // B, reps, fwd_s),
-            "host_cores_available": os.cpu_count(),
-            "numpy_spatial_conv_config1": {"ms": round(best * 1e3, 3), "pairs": int(pairs.shape[0]),
-                                           "points_per_s": round(1024 / best, 1), "numpy_threads": "BLAS default",
-                                           "note": "1 cloud x 1024 pts, 3->8 features, r=0.1, best of 10"}}
+    line["numpy_spatial_conv_config1"] = {"ms": round(best * 1e3, 3), "pairs": int(pairs.shape[0]),
+                                          "points_per_s": round(w1["P"] / best, 1), "numpy_threads": "BLAS default",
+                                          "note": "1 cloud x 1024 pts, 3->8 features, r=0.1, best of 10"}
+    return line
+
+
+def config1_inputs(w1, O):
+    """Sorted cloud, neighbour list and pdfs of config 1 from the CPU oracle (inputs of the op under test)."""
+    p1, b1, f1 = make_batch(1, w1["P"], w1["dist"], seed=0, num_features=w1["cin"])
+    r = w1["radius"]
+    mn, mx = O.compute_aabb(p1, b1, 1, True)
+    keys, idx = O.sort_points_step1(p1, b1, mn, mx, 1, r, True)
+    sp, sb, sf, cells = O.sort_points_step2(p1, b1, f1, keys, idx, mn, mx, 1, r, True)
+    start, pairs = O.find_neighbors(sp, sb, sp, cells, mn, mx, r, 1, True)
+    pdf = O.compute_pdf(sp, sb, mn, mx, start, pairs, 0.2, r, 1, True)
+    return sp, sf, sb, pdf, start, pairs, mn, mx, make_conv_weights(w1["cin"], w1["cout"], True, seed=0)
+
+
+def run_config1(args, dev, arm):
+    """BASELINE config 1: the single spatial_conv op, both arms through the same function (ops = our MCConvModule or the
+    reference's kernels).  The op's inputs (sorted cloud, neighbour list, pdfs) are precomputed: they are given."""
+    from oracle import cpu as O            # input preparation + cpu_baseline leg (checker side, not the timed path)
+    w1 = WORKLOADS[1]
+    if arm == "ours":
+        import mccnn_b200.MCConvModule as X
+    else:
+        from oracle import ref as X
+    sp, sf, sb, pdf, start, pairs, mn, mx, wts = config1_inputs(w1, O)
+    host = [sp, sf, sb, pdf, sp, start, pairs, mn, mx] + list(wts)
+    pinned = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in host]
+    res = [t.to(dev) for t in pinned]
+    attrs = (w1["cout"], True, 1, w1["radius"], True, True)
+    steps, warm = args.steps, max(args.warmup, 3)
+    flush = torch.zeros(192 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+    for _ in range(warm):
+        X.spatial_conv(*res, *attrs)
+    torch.cuda.synchronize(dev)
+    sampler = ClockSampler(dev.index).start()
+    ms = []
+    for _ in range(steps):
+        flush_l2(flush)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        X.spatial_conv(*res, *attrs)
+        e.record()
+        torch.cuda.synchronize(dev)
+        ms.append(s.elapsed_time(e))
+    dev_in = [torch.empty_like(t, device=dev) for t in pinned]
+    out_host = torch.empty((w1["P"], w1["cout"]), dtype=torch.float32).pin_memory()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        for d, h in zip(dev_in, pinned):
+            d.copy_(h, non_blocking=True)
+        out_host.copy_(X.spatial_conv(*dev_in, *attrs))
+        torch.cuda.synchronize(dev)
+    e2e_s = (time.perf_counter() - t0) / steps
+    clocks = sampler.stop()
+    t_ms = float(np.median(ms))
+    K, C, nb, nOut = int(pairs.shape[0]), w1["cin"], 3, w1["cin"] * w1["cout"]
+    alg = 12 * K + 4 * C * K + 12 * w1["P"] + 16 * w1["P"] + 4 * w1["cout"] * w1["P"] + 4 * (8 * nb * 13 + nOut * 9)
+    peak, _, src = measured_peaks()
+    line = {"metric": metric_string(w1), "value": round(w1["P"] / (t_ms * 1e-3), 1), "unit": "points/s", "n_gpus": 1,
+            "steps": steps, "warmup": warm, "ms_per_step": round(t_ms, 5), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic sphere-surface cloud (seeded), random-init weights",
+            "config": {"workload": workload_string(w1, 1), "pairs": K, "l2": "L2 flushed (192 MiB write) before every step"},
+            "clocks": clocks,
+            "e2e": {"value": round(w1["P"] / e2e_s, 1), "unit": "points/s", "ms_per_step": round(e2e_s * 1e3, 5),
+                    "h2d_bytes_per_step": int(sum(t.numel() * t.element_size() for t in pinned)),
+                    "d2h_bytes_per_step": w1["P"] * w1["cout"] * 4},
+            "roofline": {"bound": "hbm", "kernel": "spatial_conv", "achieved": round(alg / (t_ms * 1e-3) / 1e9, 2),
+                         "peak": peak, "peak_source": src, "unit": "GB/s",
+                         "frac": round(alg / (t_ms * 1e-3) / 1e9 / peak, 6), "traffic": None,
+                         "alg_bytes_per_launch": int(alg), "us_per_launch": round(t_ms * 1e3, 2)}}
+    if arm == "ours":
+        from mccnn_b200._lib import lib
+        c0 = lib.mc_launch_count()
+        X.spatial_conv(*res, *attrs)
+        per = int(lib.mc_launch_count() - c0)
+        line["gpu_launches"], line["gpu_launches_per_step"] = per * steps, per
+        from oracle import numpy_ops as NP
+        best = 1e9
+        for _ in range(10):
+            t1 = time.perf_counter()
+            NP.spatial_conv(sp, sf, sb, pdf, sp, start, pairs, mn, mx, *wts, w1["cout"], True, 1, w1["radius"], True, True)
+            best = min(best, time.perf_counter() - t1)
+        line["cpu_baseline"] = {"value": round(w1["P"] / best, 1), "unit": "points/s", "cores": os.cpu_count(),
+                                "kind": "port", "sample": "the full op (NumPy re-execution of spatial_conv, %d pairs), "
+                                "best of 10, BLAS default threads" % K}
+    else:
+        line["impl"] = "reference"
+        line["cpu_baseline"] = {"value": line["value"], "unit": "points/s", "cores": 1, "kind": "reference",
+                                "sample": "the full op; the reference's own CUDA kernel on the same GPU"}
+    return line
+
+
+def brief(res):
+    return {"ms_per_forward": round(res["latency_ms"], 4),
+            "points_per_s": round(res["points_per_step"] / (res["latency_ms"] * 1e-3), 1),
+            "pipelined": {"ms_per_step": round(res["ms_per_step"], 4), "points_per_s": round(res["value"], 1)},
+            "e2e_points_per_s": round(res["points_per_step"] / res["e2e_s"], 1),
+            "gpu_launches_per_forward": res["launches_per_forward"], "plan_overflows": res["plan_overflows"],
+            "ops": {op: {"calls": d["calls"], "us": round(d["us"], 1), "alg_bytes": int(d["alg_bytes"]),
+                         "gbs": round(d["alg_bytes"] / d["us"] * 1e-3, 1) if d["us"] > 0 else None,
+                         "frac_hbm": round(d["alg_bytes"] / d["us"] * 1e-3 / measured_peaks()[0], 4) if d["us"] > 0
+                         else None}
+                    for op, d in sorted(res["by_op"].items(), key=lambda kv: -kv[1]["us"])}}
+
+
+def run_ours(args, rank, world, dev):
+    cfg = args.config
+    w = WORKLOADS[cfg]
+    if w["kind"] == "op":
+        return run_config1(args, dev, "ours") if rank == 0 else None
+    steps, warm = args.steps, max(args.warmup, 3)
+    headline = cfg == 2
+    split = args.scaling if args.scaling else ("weak" if headline else "strong")
+    clouds = w["B"] if (world == 1 or split == "weak") else w["B"] // world
+    if clouds * world != w["B"] and split == "strong" and world > 1:
+        raise SystemExit("bench.py: %d clouds do not split evenly over %d GPUs" % (w["B"], world))
+    depth = max(1, args.pipeline if args.pipeline else (8 if w["B"] * w["P"] <= 1 << 17 else 2))
+    sampler = ClockSampler(dev.index).start()
+    res = measure_ours(w, args, rank, world, dev, clouds, split, steps, warm, depth)
+    clocks = sampler.stop()
+    strong = None
+    if headline and world > 1 and split == "weak" and w["B"] % world == 0:
+        # the strong split of ONE batch of 32 (SURVEY.md section 8e): 32 / N clouds per GPU
+        rs = measure_ours(w, args, rank, world, dev, w["B"] // world, "strong", steps, warm, depth, detail=False)
+        strong = {"clouds_per_gpu": w["B"] // world, "global_batch": w["B"], "value": round(rs["value"], 1),
+                  "unit": "points/s", "ms_per_step": round(rs["ms_per_step"], 5),
+                  "latency_ms_per_forward": round(rs["latency_ms"], 5),
+                  "e2e_points_per_s": round(rs["points_per_step"] / rs["e2e_s"], 1),
+                  "note": "ONE batch of %d clouds split contiguously over the ranks, the same %d forwards in flight, "
+                          "one all_gather of the [%d, %d] logits per step" % (w["B"], depth, w["B"], out_cols(w))}
+    if rank != 0:
+        if headline and world == 1:
+            pass
+        return None
+    roof, tens = rooflines(res, w, w["k"])
+    line = {
+        "metric": metric_string(w), "value": round(res["value"], 1), "unit": "points/s", "n_gpus": world,
+        "steps": steps, "warmup": warm, "ms_per_step": round(res["ms_per_step"], 5), "higher_is_better": True,
+        "scaling": split if world > 1 else "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic %s clouds (seeded), random-init weights" % w["dist"],
+        "config": {"workload": workload_string(w, clouds),
+                   "parallelism": "dp%d (clouds sharded, one all_gather of logits)" % world,
+                   "collective": res["gather_mode"],
+                   "concurrency": "%d forwards in flight per GPU (independent CUDA graphs on %d streams, "
+                                  "CUDA_DEVICE_MAX_CONNECTIONS=%s); every step is a complete forward of its own batch"
+                                  % (depth, depth, os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS")),
+                   "l2": res["l2"], "dynamic_sizes": res["sizes"]},
+        "clocks": clocks,
+        "latency": {"ms_per_forward": round(res["latency_ms"], 5),
+                    "points_per_s_one_at_a_time": round(res["points_per_step"] / (res["latency_ms"] * 1e-3), 1),
+                    "note": "one forward at a time, L2 flushed before each, CUDA events per step"},
+        "e2e": {"value": round(res["points_per_step"] / res["e2e_s"], 1), "unit": "points/s",
+                "ms_per_step": round(res["e2e_s"] * 1e3, 5), "h2d_bytes_per_step": int(res["h2d"]),
+                "d2h_bytes_per_step": int(res["d2h"]),
+                "one_at_a_time": {"value": round(res["points_per_step"] / res["e2e_latency_s"], 1),
+                                  "ms_per_step": round(res["e2e_latency_s"] * 1e3, 5)},
+                "note": "%d host calls in flight; each copies its batch from pinned host memory, runs the forward and "
+                        "returns logits + overflow flag to the host, every result is read on the host" % depth},
+        "gpu_launches": res["launches_per_forward"] * steps, "gpu_launches_per_step": res["launches_per_forward"],
+        "wall_s_timed_region": round(res["wall_s_timed_region"], 4), "plan_overflows": res["plan_overflows"],
+        "roofline": roof, "roofline_tensor": tens, "kernels": res["kernels"][:12],
+    }
+    if strong is not None:
+        line["scaling_strong"] = strong
+    if world == 1:
+        line["cpu_baseline"] = cpu_baseline_line(w, res["store"], res["host0"], clouds)
+        if headline and not args.no_other_configs:
+            others = {}
+            for c in (1, 3, 4, 5):
+                try:
+                    if c == 1:
+                        sub = argparse.Namespace(**{**vars(args), "steps": min(steps, 20), "config": 1})
+                        l1 = run_config1(sub, dev, "ours")
+                        others["1"] = {"workload": l1["config"]["workload"], "ms_per_step": l1["ms_per_step"],
+                                       "points_per_s": l1["value"], "e2e_points_per_s": l1["e2e"]["value"],
+                                       "roofline": l1["roofline"], "numpy_cpu": l1["cpu_baseline"]}
+                    else:
+                        wc = WORKLOADS[c]
+                        rc = measure_ours(wc, args, 0, 1, dev, wc["B"], "weak", min(steps, 10), 3, 2, detail=False)
+                        others[str(c)] = dict(workload=workload_string(wc, wc["B"]), **brief(rc))
+                    torch.cuda.empty_cache()
+                except Exception as exc:  # noqa: BLE001  (one failing configuration must not hide the headline)
+                    others[str(c)] = {"error": repr(exc)[:300]}
+            line["other_configs"] = others
+    return line
 
 
 # ----------------------------------------------------------------------------------------------- reference arm
-def run_reference(args, rank, world, dev):
-    """The reference's own CUDA kernels through the MCClassS op sequence (rank 0 only)."""
-    if rank != 0:
-        return None
-    from oracle import ref as R
-    if not R.available():
-        return {"impl": "reference", "unavailable": "oracle/_ref/libmccnn_ref.so not built (needs /root/reference)"}
-    from oracle import ref_pipeline as RP
-    from mccnn_b200 import variables  # parameter initialisation only (same seed => same weights as our arm)
-    from mccnn_b200.models import MCClassS
-    B, P, k = args.batch, args.points, args.k
-    store = variables.VariableStore(device=dev, seed=0)
-    n_batches = 4
-    host = [make_batch(B, P, "sphere", seed=i) for i in range(n_batches)]
+def measure_reference(w, dev, steps, warm):
+    """The reference's own CUDA kernels through the reference's op sequence (oracle/ref_nets.py over oracle/ref.py)."""
+    from oracle import ref as R, ref_nets
+    B = w["B"]
+    n_batches = 2
+    host = [host_batch(w, B, seed=i) for i in range(n_batches)]
     pinned = [tuple(torch.from_numpy(a).pin_memory() for a in h) for h in host]
     resident = [tuple(t.to(dev) for t in h) for h in pinned]
-    # create the variables with our builder once (names/shapes == the reference's), then hand them over as a dict
-    MCClassS.create_network(*resident[0], 1, B, k, NUM_CAT, False, 1.0, 1.0, store=store)
-    params = dict(store.vars)
+    cat = torch.from_numpy((host[0][1] % w["cats"]).astype(np.int32)).to(dev) if w["model"] == "MCSeg" else None
+    params = {}
 
     def fwd(batch):
-        return RP.mcclasss_forward(batch[0], batch[1], batch[2], 1, B, k, NUM_CAT, params)
+        inputs = {"points": batch[0], "batchIds": batch[1], "features": batch[2]}
+        if cat is not None:
+            inputs["catLabels"] = cat
+        return ref_nets.forward(w["model"], R, params, named_variable, inputs, net_args(w, B, "reference"))
 
-    steps, warm = args.steps, max(args.warmup, 3)
     for i in range(warm):
         fwd(resident[i % n_batches])
     torch.cuda.synchronize(dev)
     flush = torch.zeros(192 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
-    sampler = ClockSampler(dev.index)
-    sampler.start()
     ms = []
     for i in range(steps):
         flush_l2(flush)
@@ -563,34 +701,74 @@ def run_reference(args, rank, world, dev):
         e.record()
         torch.cuda.synchronize(dev)
         ms.append(s.elapsed_time(e))
-    clocks = sampler.stop()
-    ms_per_step = float(np.mean(ms))
-    # e2e: host buffers in, logits out
     dev_in = tuple(torch.empty_like(t, device=dev) for t in pinned[0])
-    out_host = torch.empty((B, NUM_CAT), dtype=torch.float32).pin_memory()
+    rows = B if per_cloud_output(w) else host[0][0].shape[0]
+    out_host = torch.empty((rows, out_cols(w)), dtype=torch.float32).pin_memory()
     t0 = time.perf_counter()
     for i in range(steps):
         for d, h in zip(dev_in, pinned[i % n_batches]):
             d.copy_(h, non_blocking=True)
-        out_host.copy_(fwd(dev_in)[:B])
+        out_host.copy_(fwd(dev_in)[:rows])
         torch.cuda.synchronize(dev)
     e2e_s = (time.perf_counter() - t0) / steps
-    value = B * P / (ms_per_step * 1e-3)
-    h2d = sum(t.numel() * t.element_size() for t in pinned[0])
-    return {"impl": "reference",
-            "metric": "MC-conv fwd points/sec (MCClassS, 1024 pts, batch 32 per GPU)", "value": round(value, 1),
-            "unit": "points/s", "n_gpus": 1, "launched_ranks": world, "steps": steps, "warmup": warm,
-            "ms_per_step": round(ms_per_step, 4),
+    return {"ms_per_step": float(np.mean(ms)), "e2e_s": e2e_s, "points": B * w["P"],
+            "h2d": sum(t.numel() * t.element_size() for t in pinned[0]), "d2h": rows * out_cols(w) * 4}
+
+
+def run_reference(args, rank, world, dev):
+    if rank != 0:
+        return None
+    from oracle import ref as R
+    if not R.available():
+        return {"impl": "reference", "unavailable": "oracle/_ref/libmccnn_ref.so not built (needs /root/reference)"}
+    w = WORKLOADS[args.config]
+    if w["kind"] == "op":
+        line = run_config1(args, dev, "reference")
+        line["launched_ranks"] = world
+        return line
+    steps, warm = args.steps, max(args.warmup, 3)
+    heavy = w["B"] * w["P"] > 1 << 17
+    if heavy:
+        steps, warm = min(steps, 5), 3
+    sampler = ClockSampler(dev.index).start()
+    r = measure_reference(w, dev, steps, warm)
+    clocks = sampler.stop()
+    value = r["points"] / (r["ms_per_step"] * 1e-3)
+    line = {"impl": "reference", "metric": metric_string(w), "value": round(value, 1), "unit": "points/s", "n_gpus": 1,
+            "launched_ranks": world, "steps": steps, "warmup": warm, "ms_per_step": round(r["ms_per_step"], 4),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic sphere-surface clouds (seeded), random-init weights",
-            "config": {"workload": "MCClassS forward, %d clouds x %d points, k=%d, %d classes" % (B, P, k, NUM_CAT),
-                       "path": "reference tf_ops CUDA kernels (unmodified, sm_100a) + TF-glue choreography shim"},
+            "data": "synthetic %s clouds (seeded), random-init weights" % w["dist"],
+            "config": {"workload": workload_string(w, w["B"]),
+                       "path": "reference tf_ops CUDA kernels (unmodified, sm_100a) + TF-glue choreography shim, "
+                               "reference builder / topology restated in oracle/ref_nets.py, dense glue torch/cuBLAS"},
             "clocks": clocks,
-            "e2e": {"value": round(B * P / e2e_s, 1), "unit": "points/s", "ms_per_step": round(e2e_s * 1e3, 4),
-                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": B * NUM_CAT * 4},
+            "e2e": {"value": round(r["points"] / r["e2e_s"], 1), "unit": "points/s",
+                    "ms_per_step": round(r["e2e_s"] * 1e3, 4), "h2d_bytes_per_step": int(r["h2d"]),
+                    "d2h_bytes_per_step": int(r["d2h"])},
             "cpu_baseline": {"value": round(value, 1), "unit": "points/s", "cores": 1, "kind": "reference",
                              "sample": "full workload batch per step; the reference has NO CPU implementation of this "
                                        "path -- this is its own CUDA path on the same GPU, driven by 1 host thread"}}
+    if args.config == 2 and not args.no_other_configs:
+        others = {}
+        for c in (1, 3, 4, 5):
+            try:
+                if c == 1:
+                    sub = argparse.Namespace(**{**vars(args), "steps": min(args.steps, 20), "config": 1})
+                    l1 = run_config1(sub, dev, "reference")
+                    others["1"] = {"workload": l1["config"]["workload"], "ms_per_step": l1["ms_per_step"],
+                                   "points_per_s": l1["value"], "e2e_points_per_s": l1["e2e"]["value"]}
+                else:
+                    wc = WORKLOADS[c]
+                    rc = measure_reference(wc, dev, 3, 2)
+                    others[str(c)] = {"workload": workload_string(wc, wc["B"]),
+                                      "ms_per_forward": round(rc["ms_per_step"], 3),
+                                      "points_per_s": round(rc["points"] / (rc["ms_per_step"] * 1e-3), 1),
+                                      "e2e_points_per_s": round(rc["points"] / rc["e2e_s"], 1)}
+                torch.cuda.empty_cache()
+            except Exception as exc:  # noqa: BLE001
+                others[str(c)] = {"error": repr(exc)[:300]}
+        line["other_configs"] = others
+    return line
 
 
 def main():
@@ -599,10 +777,12 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=32)
-    ap.add_argument("--points", type=int, default=1024)
-    ap.add_argument("--k", type=int, default=64)
-    ap.add_argument("--pipeline", type=int, default=8, help="forwards in flight for the throughput numbers")
+    ap.add_argument("--config", type=int, default=2, choices=sorted(WORKLOADS),
+                    help="BASELINE.json configs, 1-based (default 2: the configuration the metric is quoted on)")
+    ap.add_argument("--scaling", default=None, choices=["weak", "strong"],
+                    help="N > 1: weak = --config's batch per GPU (default for config 2), strong = one batch split")
+    ap.add_argument("--pipeline", type=int, default=0, help="forwards in flight (0: 8 for configs 2/3, 2 for 4/5)")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the other_configs block of the default line")
     args = ap.parse_args()
 
     # stdout carries exactly ONE line, the JSON: everything else any library prints there (e.g. NCCL's version banner)
@@ -617,6 +797,8 @@ def main():
     os.environ.setdefault("NCCL_MAX_NCHANNELS", os.environ.get("MCCNN_NCCL_CHANNELS", "1"))
     os.environ.setdefault("NCCL_MIN_NCHANNELS", "1")
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference" and rank != 0:
+        return                                        # the reference is single-GPU: rank 0 alone runs it
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
     dev = torch.device("cuda", local)
@@ -624,9 +806,8 @@ def main():
 
     if args.impl == "reference":
         line = run_reference(args, rank, world, dev)
-        if line is not None:
-            json_out.write(json.dumps(line) + "\n")
-            json_out.flush()
+        json_out.write(json.dumps(line) + "\n")
+        json_out.flush()
         return
 
     if world > 1:

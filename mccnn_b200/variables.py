@@ -69,8 +69,20 @@ class VariableStore:
         return {k: v.detach().cpu() for k, v in self.vars.items()}
 
     def load_state_dict(self, sd):
-        for k, v in sd.items():
-            self.vars[k] = torch.as_tensor(v, dtype=torch.float32).to(self.device).contiguous()
+        """Existing variables are overwritten IN PLACE (same storage, `_version` bumped): captured CUDA graphs, folded
+        batch-norm caches keyed on the version counters, optimizer state and `requires_grad` all stay valid.  Unknown
+        names are created."""
+        with torch.no_grad():
+            for k, v in sd.items():
+                v = torch.as_tensor(v, dtype=torch.float32)
+                cur = self.vars.get(k)
+                if cur is None:
+                    self.vars[k] = v.to(self.device).contiguous()
+                elif tuple(cur.shape) != tuple(v.shape):
+                    raise ValueError("variable %s has shape %s, the state dict holds %s" %
+                                     (k, tuple(cur.shape), tuple(v.shape)))
+                else:
+                    cur.copy_(v)
 
 
 _default = None

@@ -54,6 +54,28 @@ def test_variable_store_initialisers_follow_tensorflow():
     assert torch.equal(vs2.vars["w3"], w3)
 
 
+def test_load_state_dict_overwrites_in_place_and_refreshes_the_folded_batch_norm():
+    """Loading into a store that already ran: same storage (captured graphs / optimizer references stay valid), and
+    the folded inference batch norm sees the new statistics (its cache is keyed on the tensors' version counters)."""
+    from mccnn_b200.variables import VariableStore
+    from mccnn_b200 import MCNetworkUtils as U
+    vs = VariableStore(device="cpu", seed=0)
+    scale0, shift0 = U._bn_affine(4, False, "L_BN", vs)
+    mean = vs.vars["L_BN/moving_mean"]
+    mean.requires_grad_(False)
+    ptr = mean.data_ptr()
+    vs.load_state_dict({"L_BN/moving_mean": torch.full((4,), 5.0), "L_BN/moving_variance": torch.full((4,), 4.0),
+                        "brand_new": torch.ones(2)})
+    assert vs.vars["L_BN/moving_mean"] is mean and mean.data_ptr() == ptr
+    scale1, shift1 = U._bn_affine(4, False, "L_BN", vs)
+    want = 1.0 / np.sqrt(4.0 + U.BN_EPSILON)
+    assert np.allclose(scale1.numpy(), want) and np.allclose(shift1.numpy(), -5.0 * want)
+    assert not np.allclose(scale0.numpy(), scale1.numpy())
+    assert torch.equal(vs.vars["brand_new"], torch.ones(2))
+    with pytest.raises(ValueError):
+        vs.load_state_dict({"L_BN/moving_mean": torch.zeros(3)})
+
+
 def test_shard_ranges_partition_the_batch():
     from mccnn_b200.engine import shard_range, shard_batch
     for B in (1, 7, 32, 33):
