@@ -163,13 +163,27 @@ def test_every_op_call_of_the_forward_equals_the_reference_kernel(model):
     assert counts.get("spatial_conv", 0) >= 3 and counts.get("poisson_sampling", 0) >= 3
 
 
+# phase offsets of the reference's Poisson sampling in launch order (tf_ops/poisson_sampling.cu:192-196; SURVEY.md
+# appendix B): phase ph handles the cells with coordinates 3t + 1 + offset, i.e. cell % 3 == offset + 1 per axis
+_POOL_OFFSETS = [(1, 1, -1), (0, -1, 1), (0, 1, 1), (0, 1, 0), (0, 0, 1), (0, -1, 0), (-1, 1, -1), (0, -1, -1),
+                 (1, 0, 0), (1, -1, 1), (1, 0, 1), (-1, 1, 1), (-1, 0, 0), (1, -1, -1), (0, 1, -1), (-1, -1, 0),
+                 (-1, 1, 0), (0, 0, 0), (0, 0, -1), (1, 1, 0), (1, 0, -1), (1, -1, 0), (-1, 0, 1), (1, 1, 1),
+                 (-1, 0, -1), (-1, -1, -1), (-1, -1, 1)]
+
+
 class _CanonicalRef:
-    """The reference kernels with the within-cell order of the counting sort made the stable one (any order is a
-    valid reference output, tf_ops/sort_gpu.cu:170; the Poisson walk -- and with it the selected set -- depends on
-    it): keys, scatter, cell table, everything downstream are the reference's kernels."""
+    """The reference kernels with their two arrival-order freedoms pinned to the canonical members (any order is a
+    valid reference output; the Poisson walk -- and with it the selected SET of the next level -- depends on both):
+    the within-cell order of the counting sort (tf_ops/sort_gpu.cu:170) becomes the stable one, and the samples of a
+    (cloud, phase) launch (tf_ops/poisson_sampling.cu:115) are ordered by their position in the sorted array.  Keys,
+    scatter, cell table, sample selection and everything downstream are the reference's kernels."""
 
     def __init__(self, R, torch):
         self.R, self.torch = R, torch
+        lut = [0] * 27
+        for ph, (ox, oy, oz) in enumerate(_POOL_OFFSETS):
+            lut[(ox + 1) * 9 + (oy + 1) * 3 + (oz + 1)] = ph
+        self.lut = lut
 
     def __getattr__(self, name):
         return getattr(self.R, name)
@@ -181,6 +195,21 @@ class _CanonicalRef:
         idx = torch.empty_like(keys)
         idx[perm] = torch.arange(keys.shape[0], dtype=keys.dtype, device=keys.device)
         return keys, idx
+
+    def poisson_sampling(self, pts, bids, cells, mn, mx, radius, B, rel):
+        torch = self.torch
+        rp, rb, ri = self.R.poisson_sampling(pts, bids, cells, mn, mx, radius, B, rel)
+        n = cells.shape[1]
+        flat = cells.reshape(-1, 2).long()
+        occupied = torch.nonzero(flat[:, 1] > flat[:, 0]).reshape(-1)      # cell keys in ascending order ...
+        starts = flat[occupied, 0].contiguous()                             # ... so their ranges ascend as well
+        key = occupied[torch.searchsorted(starts, ri.long(), right=True) - 1]
+        cz, cy, cx = key % n, (key // n) % n, (key // (n * n)) % n
+        lut = torch.tensor(self.lut, device=ri.device)
+        phase = lut[(cx % 3) * 9 + (cy % 3) * 3 + (cz % 3)]
+        N = pts.shape[0]
+        order = torch.argsort((rb.reshape(-1).long() * 27 + phase) * N + ri.long())
+        return rp[order].contiguous(), rb[order].contiguous(), ri[order].contiguous()
 
 
 @pytest.mark.parametrize("model", list(CONFIGS))
