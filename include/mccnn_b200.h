@@ -193,6 +193,16 @@ int mc_mlp_rows(int numRows, const int* dNumRows, int numLayers, const int* dims
                 const float* t0, int relu0, const float* const* W, const float* const* bias,
                 const float* const* scale, const float* const* shift, const int* relu, float* y, void* stream);
 
+/* ---- dense glue on the tcgen05 tensor cores (csrc/dense_tc.cu): the same layer as mc_dense_layer for many rows,
+ * FP32 in / FP32 out through the 3xTF32 split, TMA-fed, accumulator in TMEM.  Replaces tf.matmul (cuBLAS) + the
+ * TensorFlow batch-norm / ReLU ops around it (utils/MCNetworkUtils.py:109-142).  The static operand is the weight
+ * matrix TRANSPOSED to [N, K] and split once per weight version by mc_split_tf32 into hi = tf32(w), lo = w - hi. */
+int mc_split_tf32(long long count, const float* in, float* hi, float* lo, void* stream);
+int mc_dense_layer_tc_supported(int K, int N);
+int mc_dense_layer_tc(int numRows, const int* dNumRows, int K, int N, const float* x, const float* s1, const float* t1,
+                      int relu1, const float* WtHi, const float* WtLo, const float* bias, const float* s2,
+                      const float* t2, int relu2, float* y, void* stream);
+
 /* ---- multi-GPU: the one collective of a sharded step, over NVLink peer memory (no NCCL on the data path) ----------
  * All-gather of floatsPerRank floats per rank through symmetric buffers mapped on every peer: peer stores + flag
  * words, one CTA, capturable in a CUDA graph.  peerBufPtrs: device array of worldSize buffer addresses (64-bit ints),

@@ -76,8 +76,8 @@ def _bn_affine(c, training, name, vs):
 
 
 def _dense(x, w, b, pre=None, **kw):
-    """One dense.cu launch.  A pending batch norm (+ ReLU) on the input becomes the layer's prologue; if the layer has
-    a prologue of its own (`pre`, no activation), that second affine is folded into the weights instead:
+    """One launch.  A pending batch norm (+ ReLU) on the input becomes the layer's prologue; if the layer has a prologue
+    of its own (`pre`, no activation), that second affine is folded into the weights instead:
     (a * s + t) @ W + b = a @ (s[:, None] * W) + (t @ W + b)."""
     pre_relu = False
     if isinstance(x, DeferredAffine):
@@ -85,23 +85,37 @@ def _dense(x, w, b, pre=None, **kw):
             w, b = _fold_into_weights(pre, w, b)
         pre, pre_relu, x = (x.scale, x.shift), x.relu, x.base
     nd, h = _cnt(x), _hint(x)
-    if x.shape[0] * w.shape[0] * w.shape[1] >= _LIBRARY_GEMM_MACS and not kw:
-        return _tag(_dense_library(x, w, b, pre, pre_relu, nd), nd, h)
-    return _tag(ops.dense_layer(x, w, b, pre=pre, pre_relu=pre_relu, n_dev=nd, rows_hint=h, **kw), nd, h)
+    return _tag(_layer(x, w, b, pre, pre_relu, kw.get("post"), kw.get("post_relu", False), nd, h), nd, h)
 
 
-# The dense.cu kernels are built for the latency-bound sizes of the classification networks (a few thousand rows,
-# widths <= 512).  The segmentation networks run the same 1x1 layers over every input point (MCSeg: 131 072 rows x 832
-# -> 256 = 28 GMAC): a plain large FP32 GEMM, which goes to cuBLAS (torch.addmm) exactly as the reference sends it to
-# TensorFlow's matmul; the folded batch norm + ReLU in front of it stays one own elementwise launch.
-_LIBRARY_GEMM_MACS = 1 << 27
+# Which kernel runs a layer.  Few rows (the classification heads, one row per cloud): the row kernels of dense.cu, whose
+# K loop is split over the CTA.  Everything else -- from the few-thousand-row reductions of the classification
+# networks to the per-point 1x1 layers of the segmentation networks (MCSeg: 131 072 rows x 832 -> 256 = 28 GMAC) -- is
+# a dense GEMM and runs on the tcgen05 tensor cores (dense_tc.cu, FP32 via the 3xTF32 split).  Layers the TMA path
+# cannot address (K not a multiple of 4, K < 32) stay on the FFMA tile kernel.  No library GEMM on the path.
+_TC_MIN_ROWS = 129
 
 
-def _dense_library(x, w, b, pre, pre_relu, nd):
-    def run():
-        a = x if pre is None else ops.scale_shift_act(x, pre[0], pre[1], pre_relu, nd)
-        return torch.addmm(b, a, w)
-    return _dispatch([x], run)
+def _layer(x, w, b, pre, pre_relu, post, post_relu, nd, h):
+    rows = h if h else x.shape[0]
+    if rows >= _TC_MIN_ROWS and ops.dense_layer_tc_supported(w.shape[0], w.shape[1]):
+        hi, lo = _split_weights(w)
+        return ops.dense_layer_tc(x, hi, lo, b, pre=pre, pre_relu=pre_relu, post=post, post_relu=post_relu, n_dev=nd)
+    return ops.dense_layer(x, w, b, pre=pre, pre_relu=pre_relu, post=post, post_relu=post_relu, n_dev=nd, rows_hint=h)
+
+
+_split = {}
+
+
+def _split_weights(w):
+    """Transposed tf32 hi / lo halves of a weight matrix, cached until the matrix changes (tensor._version)."""
+    key = id(w)
+    hit = _split.get(key)
+    if hit is None or hit[0] != w._version or hit[3] is not w:
+        hi, lo = ops.split_tf32_transposed(w.detach())
+        hit = (w._version, hi, lo, w)  # keeps w alive: id() stays unique
+        _split[key] = hit
+    return hit[1], hit[2]
 
 
 def _mlp(x, layers, pre=None):
@@ -121,8 +135,8 @@ def _mlp(x, layers, pre=None):
     if rows <= 128 and max(widths) <= 1024 and len(layers) <= 4:
         return _tag(ops.mlp_rows(x, layers, pre=pre, pre_relu=pre_relu, n_dev=nd), nd, h)
     for i, (w, b, post, post_relu) in enumerate(layers):
-        x = _tag(ops.dense_layer(x, w, b, pre=pre if i == 0 else None, pre_relu=pre_relu if i == 0 else False,
-                                 post=post, post_relu=post_relu, n_dev=nd, rows_hint=h), nd, h)
+        x = _tag(_layer(x, w, b, pre if i == 0 else None, pre_relu if i == 0 else False, post, post_relu, nd, h),
+                 nd, h)
     return x
 
 

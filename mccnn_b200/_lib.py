@@ -58,6 +58,10 @@ SIGNATURES = {
                                 _c_int, _ptr, _ptr]),
     "mc_mlp_rows": (_c_int, [_c_int, _ptr, _c_int, _ptr, _ptr, _ptr, _ptr, _c_int, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr,
                              _ptr]),
+    "mc_split_tf32": (_c_int, [_c_ll, _ptr, _ptr, _ptr, _ptr]),
+    "mc_dense_layer_tc_supported": (_c_int, [_c_int, _c_int]),
+    "mc_dense_layer_tc": (_c_int, [_c_int, _ptr, _c_int, _c_int, _ptr, _ptr, _ptr, _c_int, _ptr, _ptr, _ptr, _ptr, _ptr,
+                                   _c_int, _ptr, _ptr]),
     "mc_spatial_conv_grad_workspace_floats": (_c_ll, [_c_int, _c_int, _c_int, _c_int]),
     "mc_spatial_conv_grad": (_c_int, [_c_int] * 8 + [_c_float, _c_int] + [_ptr] * 25),
     "mc_sort_points_step2_grad": (_c_int, [_c_int, _c_int] + [_ptr] * 6),

@@ -315,6 +315,33 @@ def dense_layer(x, w, bias=None, pre=None, pre_relu=False, post=None, post_relu=
     return y
 
 
+def split_tf32_transposed(w):
+    """(hi, lo) halves of w TRANSPOSED to [N, K] for dense_layer_tc: hi = tf32(w^T), lo = w^T - hi."""
+    wt = _f(w).t().contiguous()
+    hi, lo = torch.empty_like(wt), torch.empty_like(wt)
+    check(lib.mc_split_tf32(wt.numel(), _p(wt), _p(hi), _p(lo), _stream()))
+    return hi, lo
+
+
+def dense_layer_tc_supported(k, n):
+    return bool(lib.mc_dense_layer_tc_supported(int(k), int(n)))
+
+
+def dense_layer_tc(x, wt_hi, wt_lo, bias=None, pre=None, pre_relu=False, post=None, post_relu=False, n_dev=None):
+    """dense_layer on the tcgen05 tensor cores; wt_hi / wt_lo [N, K] from split_tf32_transposed(w)."""
+    x, wt_hi, wt_lo = _f(x), _f(wt_hi), _f(wt_lo)
+    N, K = wt_hi.shape
+    if x.shape[1] != K:
+        raise ValueError("dense_layer_tc: input has %d columns, weights expect %d" % (x.shape[1], K))
+    y = torch.empty((x.shape[0], N), dtype=_f32, device=_dev(x))
+    s1, t1 = (None, None) if pre is None else (_f(pre[0]), _f(pre[1]))
+    s2, t2 = (None, None) if post is None else (_f(post[0]), _f(post[1]))
+    b = None if bias is None else _f(bias)
+    check(lib.mc_dense_layer_tc(x.shape[0], _p(n_dev), K, N, _p(x), _p(s1), _p(t1), int(pre_relu), _p(wt_hi), _p(wt_lo),
+                                _p(b), _p(s2), _p(t2), int(post_relu), _p(y), _stream()))
+    return y
+
+
 def mlp_rows(x, layers, pre=None, pre_relu=False, n_dev=None):
     """A whole MLP on few rows in one launch: `layers` = [(w [K, N], bias | None, post (scale, shift) | None,
     post_relu), ...]; a_0 = act(x * pre[0] + pre[1]).  Every width must be <= 1024."""
