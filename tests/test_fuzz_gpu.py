@@ -32,8 +32,14 @@ def _draw(seed):
 
 
 @pytest.mark.parametrize("seed", range(40))
-def test_random_configuration(seed):
+def test_random_configuration(seed, monkeypatch):
     import torch
+    # the sweep alternates over the kernels behind mc_spatial_conv (size-based choice, warp-level, persistent shapes)
+    variant = ["auto", "warp", "8,2", "4,4", "4,2", "4,1"][seed % 6]
+    if variant != "auto":
+        monkeypatch.setenv("MCCNN_CONV_CFG", variant)
+    else:
+        monkeypatch.delenv("MCCNN_CONV_CFG", raising=False)
     import mccnn_b200.MCConvModule as M
     from oracle import cpu as O
     c = _draw(seed)

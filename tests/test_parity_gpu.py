@@ -173,8 +173,16 @@ CONV_CASES = [
 ]
 
 
+# both kernels behind mc_spatial_conv are held to every case: the warp-level one (small convolutions), and the
+# persistent producer / consumer one in its CTA shapes "consumer warps, blocks per warp" (csrc/spatial_conv.cu picks by
+# size; MCCNN_CONV_CFG forces a variant)
+@pytest.mark.parametrize("variant", ["auto", "warp", "8,2", "4,4", "4,1", "8,1"])
 @pytest.mark.parametrize("B,N,dist,C,Co,combin,radius,avg,scaleInv", CONV_CASES)
-def test_spatial_conv(env, B, N, dist, C, Co, combin, radius, avg, scaleInv):
+def test_spatial_conv(env, monkeypatch, variant, B, N, dist, C, Co, combin, radius, avg, scaleInv):
+    if variant != "auto":
+        monkeypatch.setenv("MCCNN_CONV_CFG", variant)
+    else:
+        monkeypatch.delenv("MCCNN_CONV_CFG", raising=False)
     e = env
     O, M, T, A = e["O"], e["M"], e["T"], e["A"]
     pts, bids, feats = make_batch(B, N, dist, seed=5, num_features=C)

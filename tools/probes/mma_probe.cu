@@ -76,7 +76,29 @@ void run(const char* name, F launch, int warps, int ilp, int iters) {
     cudaFree(out); cudaFree(cyc);
 }
 
+// Does the tensor core TRUNCATE or ROUND an fp32 operand of a .tf32 mma (its low 13 mantissa bits)?  One warp, A = x at
+// [0][0], B = 1 at [0][0]; x has bits below the tf32 mantissa set so that rounding and truncation differ.
+__global__ void probe_rounding(float* out) {
+    const int lane = threadIdx.x, g = lane >> 2, t = lane & 3;
+    const float xs[4] = {1.0f + 0x1.8p-11f, 1.0f + 0x1.0p-11f, 1.0f + 0x1.fp-11f, -(1.0f + 0x1.8p-11f)};
+    for (int c = 0; c < 4; ++c) {
+        unsigned a[4] = {0, 0, 0, 0}, b[2] = {0, 0};
+        if (g == 0 && t == 0) a[0] = __float_as_uint(xs[c]);   // A[0][0]
+        if (g == 0 && t == 0) b[0] = __float_as_uint(1.0f);    // B[0][0]
+        float d[4] = {0.f, 0.f, 0.f, 0.f};
+        mma_k8(d, a, b);
+        if (lane == 0) { out[2 * c] = xs[c]; out[2 * c + 1] = d[0]; }
+    }
+}
+
 int main() {
+    {
+        float* o; cudaMalloc(&o, 64); probe_rounding<<<1, 32>>>(o); float h[8]; cudaMemcpy(h, o, 32, cudaMemcpyDeviceToHost);
+        for (int c = 0; c < 4; ++c)
+            printf("tf32 operand %.10f (%a) -> product with 1.0 = %.10f (%a): %s\n", h[2 * c], h[2 * c], h[2 * c + 1],
+                   h[2 * c + 1], h[2 * c + 1] == (float)((int)(h[2*c] * 1024.0f)) / 1024.0f ? "TRUNCATED" : "not truncated");
+        cudaFree(o);
+    }
     const int iters = 4096;
     for (int warps : {1, 4, 8, 16, 32}) {
         run("mma k8", [](float* o, long long* c, int th, int it) { probe<1, 8><<<148, th>>>(o, c, it); }, warps, 1, iters);
