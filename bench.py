@@ -213,7 +213,7 @@ def measure_ours(w, args, rank, world, dev, clouds, split, steps, warmup, depth,
     import torch.distributed as dist
     from mccnn_b200 import runtime
     from mccnn_b200._lib import lib
-    from mccnn_b200.engine import (PlannedForward, PipelinedForward, HostForward, PipelinedHostForward, PeerGather,
+    from mccnn_b200.engine import (PlannedForward, PipelinedForward, HostForward, PipelinedHostForward, PeerExchange,
                                    gather_logits, gather_point_logits, pack_batch, shard_batch)
     from mccnn_b200.profiling import OpProfile
 
@@ -250,36 +250,46 @@ def measure_ours(w, args, rank, world, dev, clouds, split, steps, warmup, depth,
     cols = out_cols(w)
     points_per_step = total_clouds * w["P"]
 
-    # ---- the step's closing collective: per-cloud logits -> an epilogue captured into each lane's graph (own kernel
-    # over NVLink peer memory, NCCL as fallback); per-point logits of unequal length -> issued behind each forward
+    # ---- the step's closing collective.  Default: put / collect over NVLink peer memory (engine.PeerExchange,
+    # csrc/peer_gather.cu): the put is the last node of each lane's CUDA graph, the collect runs on a side stream, the
+    # overflow flags travel with the rows.  Fallback (MCCNN_GATHER=nccl or no symmetric memory): NCCL all_gather,
+    # captured in the graph for the per-cloud logits, issued behind each forward for per-point logits.
     gather_mode = "none"
     after = None
-
-    def epilogues(n):
-        nonlocal gather_mode, after
-        if world == 1:
-            return None
-        if not per_cloud_output(w):
-            gather_mode = "NCCL all_gather of padded per-point logits (count prefix) issued behind each forward"
-            after = lambda out, flag: gather_point_logits(out, world)  # noqa: E731
-            return None
-        if os.environ.get("MCCNN_GATHER", "peer") == "peer":
-            try:
-                eps = [PeerGather(rows, cols, dev) for _ in range(n)]
-                gather_mode = ("all_gather of the per-cloud logits as ONE own kernel over NVLink peer memory "
-                               "(symmetric buffers, peer stores + flags; csrc/peer_gather.cu), a node of each "
-                               "lane's CUDA graph")
-                return eps
-            except Exception as exc:  # noqa: BLE001
-                sys.stderr.write("bench: peer-memory all_gather unavailable (%r); using NCCL\n" % (exc,))
-        groups = [dist.new_group(list(range(world))) for _ in range(n)]
-        gather_mode = "NCCL all_gather captured in each lane's CUDA graph (one communicator per lane)"
-        return [(lambda o, g=g: gather_logits(o, total_clouds, world, group=g)) for g in groups]
-
     if sharded and absolute:
         depth = 1  # the box all-reduce inside the forward uses the default communicator: one forward in flight
-    eps = epilogues(depth + 1)
-    eng = PlannedForward(fn, rows, use_graph=True, slack=1.3, epilogue=None if eps is None else eps[depth])
+    exs, eps, sync_ex = None, None, None
+    if world > 1:
+        cap_rows = int(max_over_ranks(rows, world, dev))
+        if os.environ.get("MCCNN_GATHER", "peer") == "peer":
+            try:
+                exs = [PeerExchange(cap_rows, cols, dev, compact=not per_cloud_output(w)) for _ in range(depth + 1)]
+                sync_ex = PeerExchange(1, 4, dev)
+                gather_mode = ("all_gather of the %s logits over NVLink peer memory (symmetric ring buffers, peer stores + "
+                               "flags; csrc/peer_gather.cu): put = last node of each lane's CUDA graph, collect %s, "
+                               "overflow flags gathered with the rows" %
+                               ("per-cloud" if per_cloud_output(w) else "per-point (unequal row counts, compacted)",
+                                "right behind it in the graph" if per_cloud_output(w) else "on a side stream"))
+            except Exception as exc:  # noqa: BLE001
+                sys.stderr.write("bench: peer-memory exchange unavailable (%r); using NCCL\n" % (exc,))
+                exs = None
+        if exs is None:
+            if per_cloud_output(w):
+                groups = [dist.new_group(list(range(world))) for _ in range(depth + 1)]
+                eps = [(lambda o, g=g: gather_logits(o, total_clouds, world, group=g)) for g in groups]
+                gather_mode = "NCCL all_gather captured in each lane's CUDA graph (one communicator per lane)"
+            else:
+                gather_mode = "NCCL all_gather of padded per-point logits (count prefix) issued behind each forward"
+                after = lambda out, flag: gather_point_logits(out, world)  # noqa: E731
+
+    def device_barrier():
+        """Ranks leave together (device side): the timed regions start within microseconds of each other."""
+        if sync_ex is not None:
+            sync_ex(torch.zeros((1, 4), dtype=torch.float32, device=dev))
+
+    in_graph = per_cloud_output(w)   # few-KB logits of a sub-0.1-ms step: collect inside the graph (one host launch)
+    eng = PlannedForward(fn, rows, use_graph=True, slack=1.3, epilogue=None if eps is None else eps[depth],
+                         exchange=None if exs is None else exs[depth], collect_in_graph=in_graph)
     eng.calibrate(resident)
     flush = torch.zeros(192 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # 192 MiB > L2
     warm = max(warmup, 3)
@@ -317,13 +327,15 @@ def measure_ours(w, args, rank, world, dev, clouds, split, steps, warmup, depth,
     pipe_res = [pack_batch(*r) for r in resident]
     for i in range(n_batches, n_pipe):
         pipe_res.append(pack_batch(*(torch.from_numpy(a).to(dev) for a in make(i))))
-    pipe = PipelinedForward(fn, rows, depth=depth, slack=1.3, epilogues=None if eps is None else eps[:depth])
+    pipe = PipelinedForward(fn, rows, depth=depth, slack=1.3, epilogues=None if eps is None else eps[:depth],
+                            exchanges=None if exs is None else exs[:depth], collect_in_graph=in_graph)
     pipe.calibrate(resident)
     for i in range(warm * depth):
         pipe.submit_packed(pipe_res[i % n_pipe], after=after)
     pipe.join()
     torch.cuda.synchronize(dev)
     barrier(world)
+    device_barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     tw0 = time.perf_counter()
     ev0.record()
@@ -354,7 +366,7 @@ def measure_ours(w, args, rank, world, dev, clouds, split, steps, warmup, depth,
     torch.cuda.synchronize(dev)
     c0 = lib.mc_launch_count()
     eager.run_async(*resident[0])
-    res["launches_per_forward"] = int(lib.mc_launch_count() - c0) + int("own kernel" in gather_mode)
+    res["launches_per_forward"] = int(lib.mc_launch_count() - c0) + (2 if exs is not None else 0)
     op_iters = min(steps, 10) if detail else 3
     tables = []
     for i in range(op_iters):
@@ -414,9 +426,12 @@ def measure_ours(w, args, rank, world, dev, clouds, split, steps, warmup, depth,
     res["checksum"] = checksum
     res["h2d"] = sum(t.numel() * t.element_size() for t in pinned[0]) * world
     out_rows_total = phf.pipe.engines[0]._out_view.shape[0]
-    res["d2h"] = (out_rows_total * cols * 4 + 4) * world
-    if after is not None:  # every rank also reads the gathered per-point logits
-        res["d2h"] += int(max_over_ranks(n_local, world, dev)) * world * cols * 4 * world
+    if exs is not None:      # every rank reads the gathered logits of all ranks + (rows, flag) per rank
+        res["d2h"] = (int(max_over_ranks(rows, world, dev)) * world * cols * 4 + 8 * world + 8) * world
+    else:
+        res["d2h"] = (out_rows_total * cols * 4 + 4) * world
+        if after is not None:
+            res["d2h"] += int(max_over_ranks(rows, world, dev)) * world * cols * 4 * world
     res["store"] = store
     res["host0"] = host[0]
     return res

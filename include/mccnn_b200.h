@@ -212,6 +212,18 @@ long long mc_allgather_rows_p2p_buffer_floats(int floatsPerRank, int worldSize);
 int mc_allgather_rows_p2p(int floatsPerRank, int rank, int worldSize, const float* local, const long long* peerBufPtrs,
                           int* stepCounter, float* out, void* stream);
 
+/* The same exchange as two kernels over a ring of `slots` steps (csrc/peer_gather.cu): mc_peer_put -- last node of a
+ * forward's graph -- stores this rank's live rows + (row count, overflow flag) into every rank's symmetric buffer and
+ * waits only for the acknowledgement of step seq - slots; mc_peer_collect -- on the stream that feeds the host copy --
+ * waits for every rank's put of the step, copies the rows out (padded or compacted in rank order: per-point logits of
+ * unequal length), reports per-rank (rows, flag), the total and the MAX flag in `meta`, and acknowledges.  Ranks may
+ * drift apart by `slots` steps before anything blocks.  state: 4 device ints, zero before the first step. */
+long long mc_peer_exchange_buffer_floats(int capRows, int cols, int worldSize, int slots);
+int mc_peer_put(int capRows, const int* dRows, int cols, int rank, int worldSize, int slots, const float* local,
+                const int* dFlag, const long long* peerBufPtrs, int* state, void* stream);
+int mc_peer_collect(int capRows, int cols, int rank, int worldSize, int slots, int compact, const long long* peerBufPtrs,
+                    int* state, float* out, int* meta, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

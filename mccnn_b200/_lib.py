@@ -68,6 +68,9 @@ SIGNATURES = {
     "mc_get_sampled_features_grad": (_c_int, [_c_int, _c_int, _c_int] + [_ptr] * 4),
     "mc_allgather_rows_p2p_buffer_floats": (_c_ll, [_c_int, _c_int]),
     "mc_allgather_rows_p2p": (_c_int, [_c_int, _c_int, _c_int, _ptr, _ptr, _ptr, _ptr, _ptr]),
+    "mc_peer_exchange_buffer_floats": (_c_ll, [_c_int, _c_int, _c_int, _c_int]),
+    "mc_peer_put": (_c_int, [_c_int, _ptr, _c_int, _c_int, _c_int, _c_int, _ptr, _ptr, _ptr, _ptr, _ptr]),
+    "mc_peer_collect": (_c_int, [_c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _ptr, _ptr, _ptr, _ptr, _ptr]),
 }
 
 

@@ -59,14 +59,25 @@ def pack_batch(pts, bids, feats, pin=False):
 
 
 class PlannedForward:
-    def __init__(self, fn, out_rows, use_graph=True, slack=1.3, multistream=True, epilogue=None):
+    def __init__(self, fn, out_rows, use_graph=True, slack=1.3, multistream=True, epilogue=None, exchange=None,
+                 collect_in_graph=False):
         """fn(points, batchIds, features) -> [>= out_rows, F] tensor; out_rows rows of it are the result.
         multistream: overlap the hierarchy / convolution-geometry / feature chains on three streams (runtime.planned).
         epilogue(result) -> tensor: applied to the out_rows result rows in every mode and CAPTURED INTO THE GRAPH with
         the forward -- the place for the closing all_gather of a sharded batch (NCCL collectives are capturable), so
-        that a multi-GPU step still costs one graph launch on the host."""
+        that a multi-GPU step still costs one graph launch on the host.
+        exchange: a PeerExchange.  The `put` of the step's rows (+ the plan's overflow flag) becomes the last node of the
+        graph; the matching `collect` is launched behind every run -- on `collect_stream` if set, so that this forward's
+        stream never waits on a peer -- and leaves (rows of all ranks, meta) in `self.gathered`.
+        collect_in_graph: capture the collect right behind the put instead (one graph launch per step and nothing else
+        on the host: the better trade for the few-KB per-cloud logits of a sub-0.1-ms step; the side-stream collect is
+        for per-point logits of multi-ms steps)."""
         self.fn = fn
         self.epilogue = epilogue
+        self.exchange = exchange
+        self.collect_in_graph = bool(collect_in_graph)
+        self.collect_stream = None
+        self.gathered = None
         self.multistream = multistream
         self.out_rows = out_rows
         self.use_graph = use_graph
@@ -89,15 +100,39 @@ class PlannedForward:
         self.graph = None
         self._shape_key = (tuple(pts.shape), tuple(feats.shape))
         self.stats["records"] += 1
-        return self._finish(out)
+        res = self._finish(out)
+        self._collect()
+        return res
 
     def _finish(self, out):
         res = out[: self.out_rows]
+        if self.exchange is not None:
+            res = res.contiguous()
+            flag = self.plan.overflow if (self.plan is not None and _rt.mode() != "exact") else None
+            self.exchange.put(res, flag=flag)
+            if self.collect_in_graph:
+                self.gathered = self.exchange.collect()
         return self.epilogue(res) if self.epilogue is not None else res
+
+    def _collect(self):
+        """The collect that matches the put just enqueued (every put needs one on every rank)."""
+        if self.exchange is None or self.collect_in_graph:
+            return
+        cs = self.collect_stream
+        if cs is None:
+            self.gathered = self.exchange.collect()
+            return
+        cs.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(cs):
+            self.gathered = self.exchange.collect()
 
     def _planned(self, pts, bids, feats):
         with _rt.planned(self.plan, pts.device, multistream=self.multistream):
             return self.fn(pts, bids, feats)
+
+    def _planned_finish(self, pts, bids, feats):
+        with _rt.planned(self.plan, pts.device, multistream=self.multistream):
+            return self._finish(self.fn(pts, bids, feats))
 
     def _capture(self, pts, bids, feats):
         _, total = _layout((pts, bids, feats))
@@ -109,12 +144,14 @@ class PlannedForward:
         side = torch.cuda.Stream(device=pts.device)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):  # warm-up outside capture (allocator, lazy module loading, NCCL communicator)
-            self._finish(self._planned(*self._static_in))
+            self._planned_finish(*self._static_in)
+            if self.exchange is not None and not self.collect_in_graph:
+                self.exchange.collect()
         torch.cuda.current_stream().wait_stream(side)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             self.plan.overflow.zero_()
-            out = self._finish(self._planned(*self._static_in))
+            out = self._planned_finish(*self._static_in)
             rows, cols = out.shape
             self._result = torch.empty((rows * cols + 1,), dtype=torch.float32, device=pts.device)
             self._out_view = self._result[: rows * cols].view(rows, cols)
@@ -144,11 +181,13 @@ class PlannedForward:
             return out, torch.zeros((1,), dtype=torch.int32, device=pts.device)
         if not self.use_graph:
             self.plan.overflow.zero_()
-            out = self._planned(pts, bids, feats)
-            return self._finish(out), self.plan.overflow
+            res = self._planned_finish(pts, bids, feats)
+            self._collect()
+            return res, self.plan.overflow
         for v, t in zip(self._static_in, (pts, bids, feats)):
             v.copy_(t, non_blocking=True)
         self.graph.replay()
+        self._collect()
         self.stats["replays"] += 1
         return self._out_view, self._flag_view
 
@@ -157,6 +196,7 @@ class PlannedForward:
         the graph's input block, one graph launch.  Requires a captured graph (call run_async once before)."""
         self._in_block.copy_(block, non_blocking=True)
         self.graph.replay()
+        self._collect()
         self.stats["replays"] += 1
         return self._out_view, self._flag_view
 
@@ -170,7 +210,7 @@ class PlannedForward:
         return out
 
     def _no_solo_repair(self):
-        if self.epilogue is not None:
+        if self.epilogue is not None or self.exchange is not None:
             raise RuntimeError("mccnn_b200: a planned capacity was exceeded on a step whose graph contains a "
                                "collective; one rank cannot re-run it alone -- re-calibrate with a larger slack")
 
@@ -250,12 +290,17 @@ class PipelinedForward:
     result(ticket) makes the caller's stream (or the host) wait for that forward only and returns
     (out, overflow_flag) device tensors, valid until the lane is reused."""
 
-    def __init__(self, fn, out_rows, depth=4, slack=1.3, multistream=True, epilogues=None):
+    def __init__(self, fn, out_rows, depth=4, slack=1.3, multistream=True, epilogues=None, exchanges=None,
+                 collect_in_graph=False):
         """epilogues: one callable per lane (see PlannedForward).  Lanes run concurrently, so collectives in them must
-        use ONE PROCESS GROUP PER LANE: an NCCL communicator may not be driven from two streams at once."""
+        use ONE PROCESS GROUP PER LANE: an NCCL communicator may not be driven from two streams at once.
+        exchanges: one PeerExchange per lane: the step's put is the last node of the lane's graph, its collect runs on
+        a per-lane side stream (the lane's next forward never waits on a peer)."""
         self.depth = depth
         self.engines = [PlannedForward(fn, out_rows, use_graph=True, slack=slack, multistream=multistream,
-                                       epilogue=None if epilogues is None else epilogues[i])
+                                       epilogue=None if epilogues is None else epilogues[i],
+                                       exchange=None if exchanges is None else exchanges[i],
+                                       collect_in_graph=collect_in_graph)
                         for i in range(depth)]
         self.streams = None
         self._events = [None] * depth
@@ -271,6 +316,9 @@ class PipelinedForward:
             e.plan, e._shape_key, e.graph = p, self.engines[0]._shape_key, None
         dev = batches[0][0].device
         self.streams = [torch.cuda.Stream(device=dev) for _ in range(self.depth)]
+        for e in self.engines:
+            if e.exchange is not None and not e.collect_in_graph:
+                e.collect_stream = torch.cuda.Stream(device=dev)
         for e, s in zip(self.engines, self.streams):  # capture every lane's graph up front
             s.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(s):
@@ -289,7 +337,8 @@ class PipelinedForward:
             # sharded batch: issued from the caller's stream it would chain every lane behind the previous one
             self._after[lane] = after(out, flag) if after is not None else None
             ev = torch.cuda.Event()
-            ev.record(s)
+            cs = self.engines[lane].collect_stream
+            ev.record(s if cs is None else cs)  # the collect stream is ordered behind the forward
         self._events[lane] = ev
         return lane
 
@@ -312,6 +361,10 @@ class PipelinedForward:
         e = self.engines[ticket]
         return e._out_view, e._flag_view
 
+    def gathered(self, ticket):
+        """(rows of all ranks, meta) of that submission's exchange (valid once result()/join() made it visible)."""
+        return self.engines[ticket].gathered
+
     def join(self):
         for ev in self._events:
             if ev is not None:
@@ -328,12 +381,14 @@ class PipelinedHostForward:
         self.device = torch.device(device)
         self._result_host = [None] * pipe.depth
         self._extra_host = [None] * pipe.depth
+        self._has_extra = [None] * pipe.depth
         self._events = [None] * pipe.depth
         self._blocks = [None] * pipe.depth
 
     def submit_packed(self, pinned_block, after=None):
         """after(out) -> device tensor (e.g. engine.gather_logits over the ranks), evaluated on the lane's stream behind
-        the forward; result() then returns ITS host copy instead of the local logits."""
+        the forward; result() then returns ITS host copy instead of the local logits.  Lanes with a PeerExchange return
+        the gathered rows of all ranks."""
         lane = self.pipe._next
         if self._blocks[lane] is not None:
             raise RuntimeError("PipelinedHostForward: %d results outstanding -- call result() on the oldest ticket "
@@ -342,18 +397,29 @@ class PipelinedHostForward:
         if self._result_host[lane] is None:
             self._result_host[lane] = torch.empty(eng._result.shape, dtype=torch.float32).pin_memory()
         self.pipe._next = (lane + 1) % self.pipe.depth
+        self._has_extra[lane] = None
         with torch.cuda.stream(s):
-            eng.run_packed(pinned_block)                                   # one H2D + one graph launch
-            self._result_host[lane].copy_(eng._result, non_blocking=True)  # one D2H: logits + overflow flag
-            if after is not None:
-                extra = after(eng._out_view)
-                if self._extra_host[lane] is None or self._extra_host[lane].shape != extra.shape:
-                    self._extra_host[lane] = torch.empty(extra.shape, dtype=extra.dtype).pin_memory()
-                self._extra_host[lane].copy_(extra, non_blocking=True)
-                extra.record_stream(s)
-            self._has_extra = after is not None
+            eng.run_packed(pinned_block)                                   # one H2D + one graph launch (+ collect)
+            last = s
+            if eng.exchange is not None:                # ONE D2H: rows of all ranks + (rows, flag) of every rank
+                last = eng.collect_stream if eng.collect_stream is not None else s
+                blk = eng.exchange.block
+                if self._extra_host[lane] is None:
+                    self._extra_host[lane] = torch.empty(blk.shape, dtype=blk.dtype).pin_memory()
+                with torch.cuda.stream(last):
+                    self._extra_host[lane].copy_(blk, non_blocking=True)
+                self._has_extra[lane] = "exchange"
+            else:
+                self._result_host[lane].copy_(eng._result, non_blocking=True)  # one D2H: logits + overflow flag
+                if after is not None:
+                    extra = after(eng._out_view)
+                    if self._extra_host[lane] is None or self._extra_host[lane].shape != extra.shape:
+                        self._extra_host[lane] = torch.empty(extra.shape, dtype=extra.dtype).pin_memory()
+                    self._extra_host[lane].copy_(extra, non_blocking=True)
+                    extra.record_stream(s)
+                    self._has_extra[lane] = "after"
             ev = torch.cuda.Event()
-            ev.record(s)
+            ev.record(last)
         self._events[lane], self._blocks[lane] = ev, pinned_block
         return lane
 
@@ -366,6 +432,19 @@ class PipelinedHostForward:
         eng = self.pipe.engines[ticket]
         rows, cols = eng._out_view.shape
         host = self._result_host[ticket]
+        if self._has_extra[ticket] == "exchange":
+            ex, blk = eng.exchange, self._extra_host[ticket]
+            n = ex.world * ex.cap_rows * ex.cols
+            out, meta = blk[:n].view(ex.world * ex.cap_rows, ex.cols), blk[n:].view(torch.int32)
+            world = ex.world
+            if int(meta[2 * world + 1]) != 0:
+                # the flags travelled with the rows: EVERY rank sees the overflow of ANY rank and stops here -- no rank
+                # returns another rank's truncated rows, and no rank re-records alone
+                eng.stats["overflows"] += 1
+                raise RuntimeError("mccnn_b200: a planned capacity was exceeded on rank(s) %s of a sharded step; "
+                                   "re-calibrate with a larger slack" %
+                                   [r for r in range(world) if int(meta[2 * r + 1]) != 0])
+            return out[: int(meta[2 * world])] if eng.exchange.compact else out
         if int(host[rows * cols:].view(torch.int32)[0]) != 0:  # planned capacity exceeded: exact re-run of this batch
             eng.stats["overflows"] += 1
             eng._no_solo_repair()
@@ -374,7 +453,7 @@ class PipelinedHostForward:
                 eng.run_async(*(v.clone() for v in eng._static_in))  # re-capture for the following steps
             self.pipe.streams[ticket].synchronize()
             return out.cpu()
-        if getattr(self, "_has_extra", False):
+        if self._has_extra[ticket] == "after":
             return self._extra_host[ticket]
         return host[: rows * cols].view(rows, cols)
 
@@ -455,6 +534,63 @@ class PeerGather:
         out = local_logits.new_empty((self.world * self.rows, self.cols))
         ops.allgather_rows_p2p(local_logits, self.ptrs, self.counter, self.rank, self.world, out)
         return out
+
+
+class PeerExchange:
+    """The closing all-gather of a sharded step as a put / collect pair over NVLink peer memory (csrc/peer_gather.cu),
+    for per-cloud logits (equal shards) and per-point logits (unequal row counts, `compact=True`) alike.
+
+      put(rows, n_dev=None, flag=None)   enqueue on the current stream (capturable: the last node of a forward's graph):
+                                         this rank's live rows + its overflow flag -> every rank's symmetric buffer;
+      collect() -> (out, meta)           enqueue on the current stream: waits for every rank's put of the step.
+                                         out [world * cap_rows, cols]: rank r's rows at r * cap_rows, or (compact) all
+                                         live rows contiguous in rank order == the order of the unsharded batch;
+                                         meta int32 [2 * world + 2]: (rows, flag) per rank, total rows, MAX of the flags.
+
+    Every put must be matched by one collect on every rank; ranks may drift apart by `slots` steps before a put blocks.
+    One instance per concurrent lane.  Construction is collective (symmetric-memory rendezvous over `group`)."""
+
+    def __init__(self, cap_rows, cols, device, slots=4, compact=False, group=None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        from ._lib import lib
+        group = dist.group.WORLD if group is None else group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.cap_rows, self.cols, self.slots, self.compact = int(cap_rows), int(cols), int(slots), bool(compact)
+        floats = int(lib.mc_peer_exchange_buffer_floats(self.cap_rows, self.cols, self.world, self.slots))
+        self.buf = symm.empty((floats,), dtype=torch.float32, device=device)
+        self.buf.zero_()
+        torch.cuda.synchronize(device)            # my flags / acks are zero before any peer can learn my address
+        self.handle = symm.rendezvous(self.buf, group)
+        ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        if len(ptrs) != self.world or any(p == 0 for p in ptrs):
+            raise RuntimeError("symmetric memory rendezvous returned no peer addresses")
+        self.ptrs = torch.tensor(ptrs, dtype=torch.int64, device=device)
+        self.state = torch.zeros((4,), dtype=torch.int32, device=device)
+        # gathered rows and meta share one block: a host consumer needs ONE device-to-host copy per step
+        n = self.world * self.cap_rows * self.cols
+        self.block = torch.zeros((n + 2 * self.world + 2,), dtype=torch.float32, device=device)
+        self.out = self.block[:n].view(self.world * self.cap_rows, self.cols)
+        self.meta = self.block[n:].view(torch.int32)
+        dist.barrier(group)
+
+    def put(self, rows, n_dev=None, flag=None):
+        from . import ops
+        if rows.dim() != 2 or rows.shape[1] != self.cols or rows.shape[0] > self.cap_rows:
+            raise ValueError("PeerExchange.put: expected at most %d rows of %d columns" % (self.cap_rows, self.cols))
+        if rows.shape[0] < self.cap_rows and n_dev is None:
+            n_dev = torch.full((1,), rows.shape[0], dtype=torch.int32, device=rows.device)
+        ops.peer_put(rows, self.ptrs, self.state, self.rank, self.world, self.slots, self.cap_rows, n_dev, flag)
+
+    def collect(self):
+        from . import ops
+        return ops.peer_collect(self.ptrs, self.state, self.rank, self.world, self.slots, self.cap_rows, self.cols,
+                                self.out, self.meta, self.compact)
+
+    def __call__(self, rows):
+        """put + collect back to back on the current stream (gathered rows inside the same graph)."""
+        self.put(rows)
+        return self.collect()[0]
 
 
 def gather_point_logits(local_logits, world_size, group=None):

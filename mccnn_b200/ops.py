@@ -380,3 +380,16 @@ def allgather_rows_p2p(local, peer_ptrs, counter, rank, world, out):
     check(lib.mc_allgather_rows_p2p(local.numel(), int(rank), int(world), _p(local), _p(peer_ptrs), _p(counter),
                                     _p(out), _stream()))
     return out
+
+
+def peer_put(local, peer_ptrs, state, rank, world, slots, cap_rows, n_dev=None, flag=None):
+    """Step of the put / collect exchange (csrc/peer_gather.cu): this rank's live rows -> every rank's symmetric buffer."""
+    local = _f(local)
+    check(lib.mc_peer_put(int(cap_rows), _p(n_dev), local.shape[1], int(rank), int(world), int(slots), _p(local),
+                          _p(flag), _p(peer_ptrs), _p(state), _stream()))
+
+
+def peer_collect(peer_ptrs, state, rank, world, slots, cap_rows, cols, out, meta, compact):
+    check(lib.mc_peer_collect(int(cap_rows), int(cols), int(rank), int(world), int(slots), int(bool(compact)),
+                              _p(peer_ptrs), _p(state), _p(out), _p(meta), _stream()))
+    return out, meta

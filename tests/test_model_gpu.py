@@ -243,6 +243,33 @@ def test_peer_gather_single_rank_group():
             xs.fill_(float(step))
             g.replay()
             assert torch.equal(out, xs)
+        # the put / collect ring (engine.PeerExchange): equal rows, then unequal live rows compacted, with the overflow
+        # flag travelling in the header; put captured in a graph, collect launched behind it
+        from mccnn_b200.engine import PeerExchange
+        px = PeerExchange(8, 40, dev)
+        for step in range(9):   # more steps than ring slots
+            assert torch.equal(px(x + step), x + step)
+        pc = PeerExchange(100, 7, dev, compact=True)
+        flag = torch.zeros((1,), dtype=torch.int32, device=dev)
+        for n in (1, 37, 100, 64):
+            rows = torch.randn((n, 7), device=dev)
+            flag.fill_(n == 37)
+            pc.put(rows, flag=flag)
+            out, meta = pc.collect()
+            m = meta.cpu().tolist()
+            assert m == [n, int(n == 37), n, int(n == 37)] and torch.equal(out[:n], rows)
+        g2 = torch.cuda.CUDAGraph()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            px.put(xs)
+            px.collect()
+        torch.cuda.current_stream().wait_stream(side)
+        with torch.cuda.graph(g2):
+            px.put(xs)
+        for step in range(9):
+            xs.fill_(float(step))
+            g2.replay()
+            assert torch.equal(px.collect()[0], xs)
     finally:
         if created:
             dist.destroy_process_group()
