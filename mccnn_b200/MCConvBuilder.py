@@ -239,12 +239,12 @@ class ConvolutionBuilder:
         vs.add_to_collection(self.decayLossCollection_, weights)
         biases = vs.get_variable(convName + '_biases', [blockSize * numBlocks], "zeros")
         weights2 = vs.get_variable(convName + '_weights2', [numBlocks, blockSize, blockSize], "glorot")
-        weights2 = weights2.reshape(blockSize, numBlocks * blockSize)
-        vs.add_to_collection(self.decayLossCollection_, weights2)
+        vs.add_to_collection(self.decayLossCollection_, weights2)  # the variable itself: a view made before
+        weights2 = weights2.reshape(blockSize, numBlocks * blockSize)  # requires_grad_() would cut its gradient
         biases2 = vs.get_variable(convName + '_biases2', [numBlocks, blockSize], "zeros").reshape(numBlocks * blockSize)
         weights3 = vs.get_variable(convName + '_weights3', [numBlocks, blockSize, blockSize], "glorot")
-        weights3 = weights3.reshape(blockSize, numBlocks * blockSize)
         vs.add_to_collection(self.decayLossCollection_, weights3)
+        weights3 = weights3.reshape(blockSize, numBlocks * blockSize)
         biases3 = vs.get_variable(convName + '_biases3', [numBlocks, blockSize], "zeros").reshape(numBlocks * blockSize)
 
         return spatial_conv(currGridTuple[0], sortFeatures, currGridTuple[1], currPDFs,

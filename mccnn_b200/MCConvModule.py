@@ -377,7 +377,17 @@ def spatial_conv_grad(inPts, inFeatures, inBatchIds, inPDFs, inSamplePts, neighS
 
 
 def _wants_grad(*tensors):
-    return torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors)
+    """True when a gradient has to flow through the op: a tensor input requires grad, or a pending inference batch
+    norm (runtime.DeferredAffine) does -- its base, scale or shift (fine-tuning through frozen statistics, evaluation
+    without no_grad): it is then materialised through differentiable torch ops instead of being folded into a kernel."""
+    if not torch.is_grad_enabled():
+        return False
+    for t in tensors:
+        if isinstance(t, torch.Tensor) and t.requires_grad:
+            return True
+        if isinstance(t, _rt.DeferredAffine) and (t.base.requires_grad or t.scale.requires_grad or t.shift.requires_grad):
+            return True
+    return False
 
 
 def _exact_only(name):
@@ -394,6 +404,7 @@ class _SortPointsStep2(torch.autograd.Function):  # MCConvModuleSrc:28-32
     @staticmethod
     def forward(ctx, inPts, inFeatures, rest):
         ctx.save_for_backward(rest[2])  # indexs
+        ctx.num_features = inFeatures.shape[1]
         p, b, f, cells = _fwd["sort_points_step2"](inPts, rest[0], inFeatures, *rest[1:])
         ctx.mark_non_differentiable(b, cells)
         return p, b, f, cells
@@ -402,6 +413,7 @@ class _SortPointsStep2(torch.autograd.Function):  # MCConvModuleSrc:28-32
     def backward(ctx, gp, gb, gf, gc):
         (indexs,) = ctx.saved_tensors
         gp = torch.zeros((indexs.shape[0], 3), device=indexs.device) if gp is None else gp
+        gf = torch.zeros((indexs.shape[0], ctx.num_features), device=indexs.device) if gf is None else gf
         ip, iF = sort_points_step2_grad(indexs, gp.contiguous(), gf.contiguous())
         return ip, iF, None
 
@@ -457,6 +469,13 @@ class _SpatialConv(torch.autograd.Function):  # MCConvModuleSrc:74-81
         return dF, dW1, dW2, dWo, db1, db2, dbo, None, None
 
 
+def _differentiable_value(a):
+    if not isinstance(a, _rt.DeferredAffine):
+        return a
+    v = a.base * a.scale + a.shift        # torch ops: the gradient reaches the base and the folded batch-norm vectors
+    return torch.relu(v) if a.relu else v
+
+
 def _differentiable(name, picks, route):
     plain = _fwd[name]
 
@@ -467,7 +486,7 @@ def _differentiable(name, picks, route):
         if kwargs or not _wants_grad(*[args[i] for i in picks if i < len(args)]):
             return plain(*args, **kwargs)
         _exact_only(name)
-        args = tuple(_rt.materialize(a) for a in args)
+        args = tuple(_differentiable_value(a) for a in args)
         return route(*args)
     return wrapper
 

@@ -2,8 +2,9 @@
 1x1 "convolution" (a matmul) and the final MLPs.  Same function names and argument lists as the reference.
 
 In the reference this layer is TensorFlow (tf.layers.batch_normalization, tf.matmul, tf.nn.relu).  Here every function
-is one launch of mccnn_b200/csrc/dense.cu per layer: inference batch norms are folded into per-column (scale, shift)
-vectors -- cached until a variable changes -- and applied in the prologue / epilogue of the layer's FP32 GEMM.
+is one launch per layer -- mccnn_b200/csrc/dense_tc.cu (tcgen05 tensor cores) for the large layers, csrc/dense.cu for
+the small ones: inference batch norms are folded into per-column (scale, shift) vectors -- cached until a variable
+changes -- and applied in the prologue / epilogue of the layer's FP32 GEMM.
 Inference (the measured path): moving mean / variance, epsilon 1e-3 as tf.layers.batch_normalization.  Training
 (isTraining=True, exact mode only): the same functions run as differentiable torch ops -- batch statistics with the
 moving averages updated at TensorFlow's momentum 0.99, dropout with keepProb -- so that, together with the autograd
@@ -89,16 +90,20 @@ def _dense(x, w, b, pre=None, **kw):
 
 
 # Which kernel runs a layer.  Few rows (the classification heads, one row per cloud): the row kernels of dense.cu, whose
-# K loop is split over the CTA.  Everything else -- from the few-thousand-row reductions of the classification
-# networks to the per-point 1x1 layers of the segmentation networks (MCSeg: 131 072 rows x 832 -> 256 = 28 GMAC) -- is
-# a dense GEMM and runs on the tcgen05 tensor cores (dense_tc.cu, FP32 via the 3xTF32 split).  Layers the TMA path
-# cannot address (K not a multiple of 4, K < 32) stay on the FFMA tile kernel.  No library GEMM on the path.
+# K loop is split over the CTA.  Large layers -- the per-point 1x1 layers of the segmentation networks (MCSeg: 131 072
+# rows x 832 -> 256 = 28 GMAC), the lower levels of MCClassH -- are dense GEMMs and run on the tcgen05 tensor cores
+# (dense_tc.cu, FP32 via the 3xTF32 split).  In between (a few thousand rows x 64..256 columns: the reductions of
+# MCClassS, 12-44 MMAC) a tcgen05 tile pipeline has 2-4 K blocks to amortise its prologue over and the latency-tuned
+# FFMA tile kernel is as fast or faster (measured 14.7 / 16.7 us against 23.7 / 17 us); it also takes the layers the TMA
+# path cannot address (K not a multiple of 4, K < 32).  No library GEMM on the path.
 _TC_MIN_ROWS = 129
+_TC_MIN_MACS = 1 << 26
 
 
 def _layer(x, w, b, pre, pre_relu, post, post_relu, nd, h):
     rows = h if h else x.shape[0]
-    if rows >= _TC_MIN_ROWS and ops.dense_layer_tc_supported(w.shape[0], w.shape[1]):
+    if (rows >= _TC_MIN_ROWS and rows * w.shape[0] * w.shape[1] >= _TC_MIN_MACS and
+            ops.dense_layer_tc_supported(w.shape[0], w.shape[1])):
         hi, lo = _split_weights(w)
         return ops.dense_layer_tc(x, hi, lo, b, pre=pre, pre_relu=pre_relu, post=post, post_relu=post_relu, n_dev=nd)
     return ops.dense_layer(x, w, b, pre=pre, pre_relu=pre_relu, post=post, post_relu=post_relu, n_dev=nd, rows_hint=h)

@@ -594,11 +594,8 @@ extern "C" int mc_poisson_sampling(int scaleInv, float radius, int numPoints, co
     MC_REQUIRE(numCells <= 1290, "mc_poisson_sampling: grid too fine (cell index would overflow)");
     MC_REQUIRE(dNumSamples != nullptr, "mc_poisson_sampling: dNumSamples required");
     cudaStream_t s = (cudaStream_t)stream;
-    static bool attrSet = false;
-    if (!attrSet) {
-        cudaFuncSetAttribute(poisson_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSelSmemBytes);
-        attrSet = true;
-    }
+    // the opt-in to more than 48 KB of dynamic shared memory is per device (and cheap): set it on every call
+    cudaFuncSetAttribute(poisson_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSelSmemBytes);
     const long long N = numPoints > 0 ? numPoints : 1;
     MC_REQUIRE(((uintptr_t)workspace) % 8 == 0, "mc_poisson_sampling: workspace must be 8-byte aligned");
     const int descInts = 2 * (batchSize + 2);

@@ -887,13 +887,7 @@ int launch_variant(ConvArgs a, int nb, cudaStream_t s) {
     const int totalRuns = cdiv(a.capM, a.G);
     const size_t fixed = (size_t)chunkBlocks * 4 * 32 * 16 + kStages * sizeof(StageHead) + (size_t)kStages * 32 * FW * 4 +
                          (a.B <= kRadiusTable ? (size_t)a.B * 4 : 0) + 16 + 2 * kStages * 8;
-    static bool attr[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 64 && !attr[dev]) {
-        cudaFuncSetAttribute(spatial_conv_kernel<MODE, NB, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        attr[dev] = true;
-    }
+    cudaFuncSetAttribute(spatial_conv_kernel<MODE, NB, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     int perSm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, spatial_conv_kernel<MODE, NB, NC>, (kProducers + NC) * 32,
                                                   fixed + 1024);

@@ -63,7 +63,12 @@ class VariableStore:
         return v
 
     def add_to_collection(self, name, value):
-        self.collections.setdefault(name, []).append(value)
+        """tf.add_to_collection; idempotent per tensor storage: the TensorFlow graph is built once, this eager code
+        runs the builder on every forward, so re-adding the same variable (or a view of it) is a no-op."""
+        coll = self.collections.setdefault(name, [])
+        ptr = value.data_ptr() if hasattr(value, "data_ptr") else id(value)
+        if all((c.data_ptr() if hasattr(c, "data_ptr") else id(c)) != ptr for c in coll):
+            coll.append(value)
 
     def state_dict(self):
         return {k: v.detach().cpu() for k, v in self.vars.items()}
