@@ -126,6 +126,31 @@ __device__ __forceinline__ void sweep_sample(int i, bool scaleInv, int n, float 
     unsigned nonEmpty = __ballot_sync(MC_FULL_MASK, hi > lo);
     const unsigned ltMask = (1u << lane) - 1u;
     int count = 0, nr = 0;
+    if (!WRITE) {
+        // Sparse neighbourhoods (fine grids: a fraction of a point per cell, e.g. MCSeg r = 0.03, ScanNet rooms): the
+        // candidate-per-lane sweep below would spend one round per non-empty cell on one or two candidates.  Instead
+        // LANE = CELL: every lane walks its own cell's few candidates and records the hits as a bit mask; the cells
+        // are the lanes in table order, so a warp prefix sum of the per-lane counts gives the same ordered slots.
+        int maxPop = hi - lo;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) maxPop = max(maxPop, __shfl_xor_sync(MC_FULL_MASK, maxPop, d));
+        if (maxPop <= 32 && maxPop < __popc(nonEmpty)) {
+            unsigned mask = 0;
+            for (int c = 0; c < maxPop; ++c) {
+                const int j = lo + c;
+                if (j < hi &&
+                    dist2_ref(sx, sy, sz, pts2[(size_t)j * 3], pts2[(size_t)j * 3 + 1], pts2[(size_t)j * 3 + 2]) <= thr)
+                    mask |= 1u << c;
+            }
+            roundsOut[lane] = make_int2(lo, (int)mask);
+            int c = __popc(mask);
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(MC_FULL_MASK, c, d);
+            outCount = c;
+            outRounds = -1;  // cached in the lane = cell format
+            return;
+        }
+    }
     while (nonEmpty) {
         const int o = __ffs(nonEmpty) - 1;
         nonEmpty &= nonEmpty - 1;
@@ -215,7 +240,21 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32)
         const int base = sh.base + sh.offset[slot];
         if (lane == 0) start[i] = base;
         const int nr = sh.nRounds[slot];
-        if (nr <= kFusedRounds) {
+        if (nr < 0) {  // lane = cell format: (first candidate, hit mask) per lane, cells in lane order
+            const int2 rd = sh.rounds[slot][lane];
+            unsigned mask = (unsigned)rd.y;
+            const int c = __popc(mask);
+            int dst = base + warp_inclusive_scan(c) - c;
+            while (mask) {
+                const int bit = __ffs(mask) - 1;
+                mask &= mask - 1;
+                if (dst < capK)
+                    pairs[dst] = make_int2(rd.x + bit, i);
+                else if (dOverflow != nullptr)
+                    *dOverflow = 1;
+                ++dst;
+            }
+        } else if (nr <= kFusedRounds) {
             int written = 0;
             for (int r = 0; r < nr; ++r) {
                 const int2 rd = sh.rounds[slot][r];

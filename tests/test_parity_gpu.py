@@ -109,6 +109,34 @@ def test_find_neighbors_bit_exact(env, B, N, dist, ragged, radius, scaleInv):
             assert np.array_equal(A(rpairs), A(gpairs))
 
 
+@pytest.mark.parametrize("B,N,dist,ragged,radius,scaleInv", CASES + [(4, 4000, "sphere", False, 0.03, True),
+                                                                      (2, 20000, "room", False, 0.1, False)])
+def test_find_neighbors_fused_bit_exact(env, B, N, dist, ragged, radius, scaleInv):
+    """The one-launch count + scan + fill kernel of the sync-free pipeline (mc_find_neighbors_fused: candidate-per-lane
+    sweep for populated cells, lane-per-cell sweep for sparse grids, decoupled look-back for the start indices) gives
+    the oracle's start indices and pair list bit for bit; a too small capacity raises the overflow flag."""
+    e = env
+    O, T, A, torch = e["O"], e["T"], e["A"], e["torch"]
+    from mccnn_b200 import ops
+    pts, bids, feats = make_batch(B, N, dist, seed=12, num_features=1, ragged=ragged)
+    mn, mx, keys, idx, sp, sb, sf, cells = _grid(e, pts, bids, feats, B, radius, scaleInv, O)
+    smp, smpb, _ = O.poisson_sampling(sp, sb, cells, mn, mx, radius * 0.5, B, scaleInv)
+    for samples, sbids in ((smp, smpb), (sp, sb)):
+        ostart, opairs = O.find_neighbors(samples, sbids, sp, cells, mn, mx, radius, B, scaleInv)
+        K = opairs.shape[0]
+        flag = torch.zeros((1,), dtype=torch.int32, device=e["dev"])
+        start, pairs, k_dev = ops.find_neighbors_fused(T(samples), T(sbids).reshape(-1), T(sp), T(cells), T(mn), T(mx),
+                                                       radius, scaleInv, K + 64, overflow=flag)
+        assert int(k_dev.item()) == K and int(flag.item()) == 0
+        assert np.array_equal(A(start), ostart.reshape(-1))
+        assert np.array_equal(A(pairs)[:K], opairs)
+        if K > 8:
+            flag.zero_()
+            ops.find_neighbors_fused(T(samples), T(sbids).reshape(-1), T(sp), T(cells), T(mn), T(mx), radius, scaleInv,
+                                     K - 5, overflow=flag)
+            assert int(flag.item()) == 1
+
+
 @pytest.mark.parametrize("B,N,dist,ragged,radius,scaleInv", CASES)
 def test_poisson_bit_exact(env, B, N, dist, ragged, radius, scaleInv):
     e = env
