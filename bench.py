@@ -488,7 +488,13 @@ def cpu_baseline_line(w, store, host_batch_, clouds):
             "host_cores_available": os.cpu_count()}
     # config 1: single spatial_conv, 1 cloud x 1024 points, 3 -> 8 features, r = 0.1
     w1 = WORKLOADS[1]
-    sp, sf, sb, pdf, start, pairs, mn, mx, wts = config1_inputs(w1, O)
+    p1, b1, f1 = make_batch(1, w1["P"], w1["dist"], seed=0, num_features=w1["cin"])
+    mn, mx = O.compute_aabb(p1, b1, 1, True)
+    keys, idx = O.sort_points_step1(p1, b1, mn, mx, 1, w1["radius"], True)
+    sp, sb, sf, cells = O.sort_points_step2(p1, b1, f1, keys, idx, mn, mx, 1, w1["radius"], True)
+    start, pairs = O.find_neighbors(sp, sb, sp, cells, mn, mx, w1["radius"], 1, True)
+    pdf = O.compute_pdf(sp, sb, mn, mx, start, pairs, 0.2, w1["radius"], 1, True)
+    wts = make_conv_weights(w1["cin"], w1["cout"], True, seed=0)
     best = 1e9
     for _ in range(10):
         t1 = time.perf_counter()
@@ -500,31 +506,31 @@ def cpu_baseline_line(w, store, host_batch_, clouds):
     return line
 
 
-def config1_inputs(w1, O):
-    """Sorted cloud, neighbour list and pdfs of config 1 from the CPU oracle (inputs of the op under test)."""
-    p1, b1, f1 = make_batch(1, w1["P"], w1["dist"], seed=0, num_features=w1["cin"])
+def config1_inputs(w1, X, dev):
+    """Sorted cloud, neighbour list and pdfs of config 1 -- the inputs of the op under test -- made with the arm's own
+    ops (X = mccnn_b200.MCConvModule or oracle.ref; the two agree bit for bit on the indices).  Torch CUDA tensors."""
+    p1, b1, f1 = (torch.from_numpy(a).to(dev) for a in make_batch(1, w1["P"], w1["dist"], seed=0, num_features=w1["cin"]))
     r = w1["radius"]
-    mn, mx = O.compute_aabb(p1, b1, 1, True)
-    keys, idx = O.sort_points_step1(p1, b1, mn, mx, 1, r, True)
-    sp, sb, sf, cells = O.sort_points_step2(p1, b1, f1, keys, idx, mn, mx, 1, r, True)
-    start, pairs = O.find_neighbors(sp, sb, sp, cells, mn, mx, r, 1, True)
-    pdf = O.compute_pdf(sp, sb, mn, mx, start, pairs, 0.2, r, 1, True)
-    return sp, sf, sb, pdf, start, pairs, mn, mx, make_conv_weights(w1["cin"], w1["cout"], True, seed=0)
+    mn, mx = X.compute_aabb(p1, b1, 1, True)
+    keys, idx = X.sort_points_step1(p1, b1, mn, mx, 1, r, True)
+    sp, sb, sf, cells = X.sort_points_step2(p1, b1, f1, keys, idx, mn, mx, 1, r, True)
+    start, pairs = X.find_neighbors(sp, sb, sp, cells, mn, mx, r, 1, True)
+    pdf = X.compute_pdf(sp, sb, mn, mx, start, pairs, 0.2, r, 1, True)
+    wts = tuple(torch.from_numpy(a).to(dev) for a in make_conv_weights(w1["cin"], w1["cout"], True, seed=0))
+    return sp, sf, sb, pdf, start, pairs, mn, mx, wts
 
 
 def run_config1(args, dev, arm):
     """BASELINE config 1: the single spatial_conv op, both arms through the same function (ops = our MCConvModule or the
     reference's kernels).  The op's inputs (sorted cloud, neighbour list, pdfs) are precomputed: they are given."""
-    from oracle import cpu as O            # input preparation + cpu_baseline leg (checker side, not the timed path)
     w1 = WORKLOADS[1]
     if arm == "ours":
         import mccnn_b200.MCConvModule as X
     else:
         from oracle import ref as X
-    sp, sf, sb, pdf, start, pairs, mn, mx, wts = config1_inputs(w1, O)
-    host = [sp, sf, sb, pdf, sp, start, pairs, mn, mx] + list(wts)
-    pinned = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in host]
-    res = [t.to(dev) for t in pinned]
+    sp, sf, sb, pdf, start, pairs, mn, mx, wts = config1_inputs(w1, X, dev)
+    res = [t.contiguous() for t in (sp, sf, sb, pdf, sp, start, pairs, mn, mx) + wts]
+    pinned = [t.cpu().pin_memory() for t in res]
     attrs = (w1["cout"], True, 1, w1["radius"], True, True)
     steps, warm = args.steps, max(args.warmup, 3)
     flush = torch.zeros(192 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
@@ -574,11 +580,12 @@ def run_config1(args, dev, arm):
         X.spatial_conv(*res, *attrs)
         per = int(lib.mc_launch_count() - c0)
         line["gpu_launches"], line["gpu_launches_per_step"] = per * steps, per
-        from oracle import numpy_ops as NP
+        from oracle import numpy_ops as NP   # cpu_baseline leg: NumPy re-execution of the op on the host
+        host = [t.numpy() for t in pinned]
         best = 1e9
         for _ in range(10):
             t1 = time.perf_counter()
-            NP.spatial_conv(sp, sf, sb, pdf, sp, start, pairs, mn, mx, *wts, w1["cout"], True, 1, w1["radius"], True, True)
+            NP.spatial_conv(*host, w1["cout"], True, 1, w1["radius"], True, True)
             best = min(best, time.perf_counter() - t1)
         line["cpu_baseline"] = {"value": round(w1["P"] / best, 1), "unit": "points/s", "cores": os.cpu_count(),
                                 "kind": "port", "sample": "the full op (NumPy re-execution of spatial_conv, %d pairs), "

@@ -114,6 +114,14 @@ int mc_find_neighbors_fused(int scaleInv, int numSamples, const int* dNumSamples
                             const float* samples, const int* sampleBatchIds, const float* pts2, const int* cellIdx,
                             const float* aabbMin, const float* aabbMax, int* startIdx, int* workspace, int* pairs,
                             int capacityPairs, int* dNumNeighbors, int* dOverflow, void* stream);
+/* mc_find_neighbors_fused + mc_compute_pdf in the same launch (countNeighborsCPU + packNeighborsCPU,
+ * tf_ops/find_neighbors.cc:45-78, and computeDPFsCPU, tf_ops/compute_pdf.cc:43-55): pdfs[capacityPairs] receives exactly
+ * the values mc_compute_pdf would produce for the pair list (same terms, same order). */
+int mc_find_neighbors_pdf_fused(int scaleInv, float window, int numSamples, const int* dNumSamples, int numCells,
+                                float radius, const float* samples, const int* sampleBatchIds, const float* pts2,
+                                const int* cellIdx, const float* aabbMin, const float* aabbMax, int* startIdx,
+                                int* workspace, int* pairs, float* pdfs, int capacityPairs, int* dNumNeighbors,
+                                int* dOverflow, void* stream);
 
 /* computeDPFsCPU -- tf_ops/compute_pdf.cc:43-55, tf_ops/compute_pdf.cu:98-120 */
 int mc_compute_pdf(int scaleInv, float window, int numSamples, const int* dNumSamples, int numNeighbors,

@@ -12,11 +12,12 @@ TensorFlow graph.
 Both classes work unchanged inside mccnn_b200.runtime.record()/planned(): the op wrappers they call carry the live
 row counts on the device, so a planned run issues no host synchronisation at all.
 """
+import os
 import torch
 
 from .MCConvModule import (compute_aabb, sort_points_step1, sort_points_step2, sort_features, sort_features_back,
                            compute_pdf, poisson_sampling, get_sampled_features, spatial_conv, get_block_size,
-                           transform_indexs, find_neighbors, sort_points)
+                           transform_indexs, find_neighbors, sort_points, find_neighbors_pdf)
 from . import runtime as _rt
 from . import variables as _vars
 
@@ -26,6 +27,14 @@ VERBOSE = False
 def _log(msg):
     if VERBOSE:
         print(msg)
+
+
+# MCCNN_FUSE_PDF=1: a planned run issues find_neighbors + compute_pdf of a new neighbour list as ONE launch
+# (MCConvModule.find_neighbors_pdf).  Measured and left off: timed alone the fused call is 1.2-1.5x faster for
+# <= 8k samples, but inside the forward's multi-stream graph the separate density kernel overlaps the other branch
+# and the fused kernel lengthens the critical path (MCClassS 32 x 1024: 0.237 -> 0.252 ms per forward, 376 -> 361 M
+# points/s; profiles/r2_neighbors_pdf_fused.txt).
+FUSE_NEIGHBORS_PDF = os.environ.get("MCCNN_FUSE_PDF", "0") == "1"
 
 
 class _LazyList:
@@ -203,6 +212,16 @@ class ConvolutionBuilder:
 
         if keyNeighs in self.cacheNeighs_:
             currNeighTuple = self.cacheNeighs_[keyNeighs]
+        elif FUSE_NEIGHBORS_PDF and currUsePDF and keyPDF not in self.cachePDFs_:
+            # neither the neighbour list nor its densities exist yet (utils/MCConvBuilder.py:365-386 issues
+            # find_neighbors, then compute_pdf): one fused launch in planned mode.  Off by default -- see above.
+            startIndexs, packedNeighs, pdfs = find_neighbors_pdf(
+                currOutPointHierarchy.points_[currOutPointLevel], currOutPointHierarchy.batchIds_[currOutPointLevel],
+                currGridTuple[0], currGridTuple[1], currGridTuple[2], ph.aabbMin_, ph.aabbMax_, convRadius,
+                currKDEWindow, ph.batchSize_, currRelativeRadius)
+            currNeighTuple = (startIndexs, packedNeighs)
+            self.cacheNeighs_[keyNeighs] = currNeighTuple
+            self.cachePDFs_[keyPDF] = pdfs
         else:
             startIndexs, packedNeighs = find_neighbors(
                 currOutPointHierarchy.points_[currOutPointLevel], currOutPointHierarchy.batchIds_[currOutPointLevel],

@@ -20,7 +20,7 @@ from .runtime import count_of as _cnt, tag as _tag
 
 __all__ = ["compute_aabb", "sort_points_step1", "sort_points_step2", "sort_features", "sort_features_back",
            "transform_indexs", "find_neighbors", "compute_pdf", "poisson_sampling", "get_sampled_features",
-           "spatial_conv", "get_block_size", "sort_points"]
+           "spatial_conv", "get_block_size", "sort_points", "find_neighbors_pdf"]
 
 
 def _req(cond, msg):
@@ -213,6 +213,35 @@ def find_neighbors(inPts, inBatchIds, inPts2, cellIndexs, aabbMin, aabbMax, radi
     pairs = ops.find_neighbors_pack(inPts, bids, inPts2, cellIndexs, aabbMin, aabbMax, radius, scaleInv, start, ws,
                                     K, md)
     return start.reshape(-1, 1), pairs
+
+
+@_scheduled
+def find_neighbors_pdf(inPts, inBatchIds, inPts2, inBatchIds2, cellIndexs, aabbMin, aabbMax, radius, window, batchSize,
+                       scaleInv):
+    """find_neighbors followed by compute_pdf on its result (the only way the builder uses them for a new neighbour
+    list, utils/MCConvBuilder.py:365-386) -> (startIndexs [M,1], neighIndexs [K,2], pdfs [K,1]).
+
+    Not part of the reference API: an extension that lets a planned (sync-free) run issue both as ONE kernel launch
+    (mc_find_neighbors_pdf_fused: the densities are evaluated while a sample's neighbour list is at hand).  The values
+    are bit-identical to the two separate ops; in exact / record mode it simply calls them."""
+    if _rt.mode() != "planned":
+        start, pairs = find_neighbors(inPts, inBatchIds, inPts2, cellIndexs, aabbMin, aabbMax, radius, batchSize, scaleInv)
+        return start, pairs, compute_pdf(inPts2, inBatchIds2, aabbMin, aabbMax, start, pairs, window, radius, batchSize,
+                                         scaleInv)
+    _req(radius > 0.0 and window > 0.0, "FindNeighborsOp / ComputePDFOp expect a positive radius and window")
+    _req(batchSize > 0, "FindNeighborsOp expects a positive batch size")
+    _req(inPts.dim() == 2 and inPts.shape[1] == 3 and inPts2.dim() == 2 and inPts2.shape[1] == 3,
+         "FindNeighborsOp expects points with three components")
+    _check_bids(inBatchIds, inPts.shape[0], "FindNeighborsOp")
+    _req(cellIndexs.dim() == 5 and cellIndexs.shape[0] == batchSize,
+         "FindNeighborsOp expects a five dimension tensor for the cell indices")
+    _check_aabb(aabbMin, aabbMax, batchSize, "FindNeighborsOp")
+    md = _cnt(inPts)
+    plan = _rt.current_plan()
+    start, pairs, pdf, k_dev = ops.find_neighbors_pdf_fused(inPts, inBatchIds.reshape(-1), inPts2, cellIndexs, aabbMin,
+                                                            aabbMax, radius, window, scaleInv, plan.next_capacity(), md,
+                                                            plan.overflow)
+    return _tag(start.reshape(-1, 1), md), _tag(pairs, k_dev), _tag(pdf.reshape(-1, 1), k_dev)
 
 
 @_scheduled

@@ -44,6 +44,8 @@ SIGNATURES = {
                                         _ptr, _ptr, _ptr, _c_int, _ptr, _ptr]),
     "mc_find_neighbors_fused": (_c_int, [_c_int, _c_int, _ptr, _c_int, _c_float, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr,
                                          _ptr, _ptr, _ptr, _c_int, _ptr, _ptr, _ptr]),
+    "mc_find_neighbors_pdf_fused": (_c_int, [_c_int, _c_float, _c_int, _ptr, _c_int, _c_float, _ptr, _ptr, _ptr, _ptr, _ptr,
+                                             _ptr, _ptr, _ptr, _ptr, _ptr, _c_int, _ptr, _ptr, _ptr]),
     "mc_compute_pdf": (_c_int, [_c_int, _c_float, _c_int, _ptr, _c_int, _ptr, _c_float, _ptr, _ptr, _ptr, _ptr, _ptr,
                                 _ptr, _ptr, _ptr]),
     "mc_poisson_workspace_ints": (_c_ll, [_c_int, _c_int]),

@@ -97,6 +97,24 @@ __device__ __forceinline__ float dist2_ref(float px, float py, float pz, float q
     return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
 }
 
+// One term of the kernel density estimate (compute_pdf): exp(-0.5 |d|^2 / (r h)^2) = 2^(|d|^2 e2) with
+// e2 = -0.5 log2(e) / (r h)^2, evaluated on the SFU.  Shared by pdf_kernel and the fused neighbour + pdf kernel so that
+// both produce the same bits (explicit contraction: no dependence on the compiler's choice per kernel).
+__device__ __forceinline__ float pdf_term(float dx, float dy, float dz, float e2) {
+    const float d2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(__fmul_rn(d2, e2)));
+    return y;
+}
+__device__ __forceinline__ float pdf_exponent_scale(float r, float window) {
+    const float invRadH = 1.0f / (r * window);
+    return -0.72134752044448170368f * invRadH * invRadH;
+}
+__device__ __forceinline__ float pdf_finish(float acc, float window, int k) {
+    const float g = (1.0f / window) * 0.39894228f;
+    return (acc * (g * g * g)) / (float)k;
+}
+
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
 __device__ __forceinline__ int warp_inclusive_scan(int v) {
@@ -130,6 +148,10 @@ void set_error(const char* fmt, ...);
 int check_launch(const char* what);  // cudaPeekAtLastError -> status + message; counts one kernel launch
 void count_launches(int n);          // additional kernel launches of the calling entry point
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+// pdf.cu: compute_pdf over a pair list whose batch ids are the samples' (used by mc_find_neighbors_pdf_fused)
+int launch_pdf_by_sample(bool scaleInv, float window, float radius, const int* dM, int capM, const int* dK, int capK,
+                         const float* pts, const int* sampleBids, const float* mn, const float* mx, const int* start,
+                         const int* pairs, float* pdf, cudaStream_t s);
 }  // namespace mc
 
 #define MC_REQUIRE(cond, ...)          \

@@ -8,6 +8,8 @@
 // the reference's (cells in table order find_neighbors.cu:282-291, ascending j inside a cell).  The predicate is
 // the float-exact one in common.cuh.  The total stays on the device (dNumNeighbors); the caller decides whether to
 // read it (exact-shape API) or to keep going with a capacity-sized pair buffer (sync-free pipeline).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "lookback.cuh"
 #include "scan.cuh"
@@ -89,6 +91,8 @@ constexpr int kFusedPerWarp = 4;
 constexpr int kFusedPerCta = kWarpsPerCta * kFusedPerWarp;  // 32 samples per CTA
 constexpr int kFusedRounds = 64;                            // cached hit rounds per sample (else: re-sweep)
 static_assert(kFusedPerCta == 32, "the CTA scan of the per-sample counts uses one warp");
+
+constexpr int kPdfList = 256;  // neighbour coordinates a warp keeps in shared memory for the fused density estimate
 
 struct FusedShared {
     int2 rounds[kFusedPerCta][kFusedRounds];  // (first candidate of the round, hit mask)
@@ -184,17 +188,22 @@ __device__ __forceinline__ void sweep_sample(int i, bool scaleInv, int n, float 
 
 // PER_WARP samples per warp: 1 keeps the per-warp serial chain short when there are few samples (latency bound),
 // 4 keeps the look-back chain short when there are many.
-template <int PER_WARP>
+// PDF: also evaluate compute_pdf for the pairs of every sample while its neighbour list is at hand (window > 0): the
+// same terms in the same order as pdf_kernel (common.cuh::pdf_term), so the values are bit-identical to the separate op.
+template <int PER_WARP, bool PDF>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
     neighbors_fused_kernel(bool scaleInv, const int* __restrict__ dM, int capM, int n, float radius,
                            const float* __restrict__ samples, const int* __restrict__ sbids,
                            const float* __restrict__ pts2, const int2* __restrict__ cellIdx,
                            const float* __restrict__ mn, const float* __restrict__ mx, unsigned long long* desc,
                            int numCtas, int* __restrict__ start, int2* __restrict__ pairs, int capK,
-                           int* __restrict__ dNumNeighbors, int* __restrict__ dOverflow) {
+                           int* __restrict__ dNumNeighbors, int* __restrict__ dOverflow, float window,
+                           float* __restrict__ pdfs) {
     constexpr int kFusedPerWarp = PER_WARP;
     constexpr int kPerCta = kWarpsPerCta * PER_WARP;
     __shared__ FusedShared sh;
+    __shared__ float sPx[PDF ? kWarpsPerCta : 1][PDF ? kPdfList : 1], sPy[PDF ? kWarpsPerCta : 1][PDF ? kPdfList : 1],
+        sPz[PDF ? kWarpsPerCta : 1][PDF ? kPdfList : 1];
     const int M = live_count(dM, capM);
     const int lane = lane_id(), warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) sh.cta = lookback_ticket(desc);
@@ -273,6 +282,46 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32)
             sweep_sample<true>(i, scaleInv, n, radius, samples, sbids, pts2, cellIdx, mn, mx, lane, nullptr, cnt, nr2, base,
                                pairs, capK, dOverflow);
         }
+        if (PDF) {
+            // density estimate of this sample's pairs: pdf_p = (1/k) sum_q g(x_q - x_p) over ALL k neighbours, q in list
+            // order.  The warp re-reads the neighbour indices it has just written, keeps up to kPdfList coordinates in
+            // shared memory (longer lists: the tail through L1 / L2) and every lane takes the pairs lane, lane + 32, ...
+            __syncwarp();
+            const int k = sh.count[slot];
+            const int kw = max(0, min(k, capK - base));  // pairs actually written
+            const float ext = max_extent(mn, mx, sbids[i]);
+            const float e2 = pdf_exponent_scale(scaleInv ? radius * ext : radius, window);
+            const int staged = min(kw, kPdfList);
+            for (int t = lane; t < staged; t += 32) {
+                const int j = pairs[base + t].x;
+                sPx[warp][t] = pts2[(size_t)j * 3];
+                sPy[warp][t] = pts2[(size_t)j * 3 + 1];
+                sPz[warp][t] = pts2[(size_t)j * 3 + 2];
+            }
+            __syncwarp();
+            for (int t = lane; t < kw; t += 32) {
+                float xj, yj, zj;
+                if (t < staged) {
+                    xj = sPx[warp][t];
+                    yj = sPy[warp][t];
+                    zj = sPz[warp][t];
+                } else {
+                    const int j = pairs[base + t].x;
+                    xj = pts2[(size_t)j * 3];
+                    yj = pts2[(size_t)j * 3 + 1];
+                    zj = pts2[(size_t)j * 3 + 2];
+                }
+                float acc = 0.0f;
+                for (int q = 0; q < staged; ++q) acc += pdf_term(sPx[warp][q] - xj, sPy[warp][q] - yj, sPz[warp][q] - zj, e2);
+                for (int q = staged; q < kw; ++q) {
+                    const int jj = pairs[base + q].x;
+                    acc += pdf_term(pts2[(size_t)jj * 3] - xj, pts2[(size_t)jj * 3 + 1] - yj, pts2[(size_t)jj * 3 + 2] - zj,
+                                    e2);
+                }
+                pdfs[base + t] = pdf_finish(acc, window, k);
+            }
+            __syncwarp();
+        }
     }
 }
 
@@ -291,6 +340,52 @@ extern "C" long long mc_find_neighbors_workspace_ints(int numSamples) {
 // pair capacity up front (sync-free pipeline).  startIdx receives the final start indices, *dNumNeighbors the total;
 // pairs past capacityPairs are dropped and *dOverflow is set.  workspace: mc_find_neighbors_workspace_ints, 8-byte
 // aligned.
+constexpr int kPdfFuseMaxSamples = 8192;
+
+// MCCNN_PDF_FUSE_MAX=<samples> overrides the threshold (0: always two launches) -- measurement knob.
+static int pdf_fuse_max_samples() {
+    static const int v = [] {
+        const char* e = getenv("MCCNN_PDF_FUSE_MAX");
+        return e ? atoi(e) : kPdfFuseMaxSamples;
+    }();
+    return v;
+}
+
+static int launch_fused(int scaleInv, int numSamples, const int* dNumSamples, int numCells, float radius,
+                        const float* samples, const int* sampleBatchIds, const float* pts2, const int* cellIdx,
+                        const float* aabbMin, const float* aabbMax, int* startIdx, int* workspace, int* pairs,
+                        int capacityPairs, int* dNumNeighbors, int* dOverflow, float window, float* pdfs, void* stream,
+                        const char* what) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (numSamples <= 0) {
+        cudaMemsetAsync(dNumNeighbors, 0, sizeof(int), s);
+        return check_launch(what);
+    }
+    const bool few = numSamples <= 16384;
+    const int ctas = cdiv(numSamples, few ? kWarpsPerCta : kFusedPerCta);
+    unsigned long long* desc = reinterpret_cast<unsigned long long*>(workspace);
+    cudaMemsetAsync(desc, 0, sizeof(unsigned long long) * (size_t)(ctas + 1), s);
+    const int2* cells = reinterpret_cast<const int2*>(cellIdx);
+    int2* prs = reinterpret_cast<int2*>(pairs);
+#define MC_LAUNCH_FUSED(PW, PDF)                                                                                      \
+    neighbors_fused_kernel<PW, PDF><<<ctas, kWarpsPerCta * 32, 0, s>>>(                                               \
+        scaleInv != 0, dNumSamples, numSamples, numCells, radius, samples, sampleBatchIds, pts2, cells, aabbMin, aabbMax, \
+        desc, ctas, startIdx, prs, capacityPairs, dNumNeighbors, dOverflow, window, pdfs)
+    if (pdfs != nullptr) {
+        if (few) MC_LAUNCH_FUSED(1, true);
+        else MC_LAUNCH_FUSED(kFusedPerWarp, true);
+    } else {
+        if (few) MC_LAUNCH_FUSED(1, false);
+        else MC_LAUNCH_FUSED(kFusedPerWarp, false);
+    }
+#undef MC_LAUNCH_FUSED
+    return check_launch(what);
+}
+
+// countNeighborsCPU + packNeighborsCPU (tf_ops/find_neighbors.cu:268-371) in ONE launch, for callers that provide a
+// pair capacity up front (sync-free pipeline).  startIdx receives the final start indices, *dNumNeighbors the total;
+// pairs past capacityPairs are dropped and *dOverflow is set.  workspace: mc_find_neighbors_workspace_ints, 8-byte
+// aligned.
 extern "C" int mc_find_neighbors_fused(int scaleInv, int numSamples, const int* dNumSamples, int numCells,
                                        float radius, const float* samples, const int* sampleBatchIds,
                                        const float* pts2, const int* cellIdx, const float* aabbMin,
@@ -300,26 +395,38 @@ extern "C" int mc_find_neighbors_fused(int scaleInv, int numSamples, const int* 
     MC_REQUIRE(numCells > 0, "mc_find_neighbors: cell count must be positive");
     MC_REQUIRE(dNumNeighbors != nullptr, "mc_find_neighbors_fused: dNumNeighbors required");
     MC_REQUIRE(((uintptr_t)workspace) % 8 == 0, "mc_find_neighbors_fused: workspace must be 8-byte aligned");
-    cudaStream_t s = (cudaStream_t)stream;
-    if (numSamples <= 0) {
-        cudaMemsetAsync(dNumNeighbors, 0, sizeof(int), s);
-        return check_launch("mc_find_neighbors_fused");
-    }
-    const bool few = numSamples <= 16384;
-    const int ctas = cdiv(numSamples, few ? kWarpsPerCta : kFusedPerCta);
-    unsigned long long* desc = reinterpret_cast<unsigned long long*>(workspace);
-    cudaMemsetAsync(desc, 0, sizeof(unsigned long long) * (size_t)(ctas + 1), s);
-    const int2* cells = reinterpret_cast<const int2*>(cellIdx);
-    int2* prs = reinterpret_cast<int2*>(pairs);
-    if (few)
-        neighbors_fused_kernel<1><<<ctas, kWarpsPerCta * 32, 0, s>>>(
-            scaleInv != 0, dNumSamples, numSamples, numCells, radius, samples, sampleBatchIds, pts2, cells, aabbMin,
-            aabbMax, desc, ctas, startIdx, prs, capacityPairs, dNumNeighbors, dOverflow);
-    else
-        neighbors_fused_kernel<kFusedPerWarp><<<ctas, kWarpsPerCta * 32, 0, s>>>(
-            scaleInv != 0, dNumSamples, numSamples, numCells, radius, samples, sampleBatchIds, pts2, cells, aabbMin,
-            aabbMax, desc, ctas, startIdx, prs, capacityPairs, dNumNeighbors, dOverflow);
-    return check_launch("mc_find_neighbors_fused");
+    return launch_fused(scaleInv, numSamples, dNumSamples, numCells, radius, samples, sampleBatchIds, pts2, cellIdx,
+                        aabbMin, aabbMax, startIdx, workspace, pairs, capacityPairs, dNumNeighbors, dOverflow, 0.f,
+                        nullptr, stream, "mc_find_neighbors_fused");
+}
+
+// The same launch also evaluating computeDPFsCPU (tf_ops/compute_pdf.cu:98-120) for every pair while the sample's
+// neighbour list is at hand: pdfs[capacityPairs] receives exactly the values mc_compute_pdf would produce (same terms,
+// same order).  The samples' batch ids stand in for the neighbours' (a neighbour lies in its sample's cloud).
+extern "C" int mc_find_neighbors_pdf_fused(int scaleInv, float window, int numSamples, const int* dNumSamples,
+                                           int numCells, float radius, const float* samples,
+                                           const int* sampleBatchIds, const float* pts2, const int* cellIdx,
+                                           const float* aabbMin, const float* aabbMax, int* startIdx, int* workspace,
+                                           int* pairs, float* pdfs, int capacityPairs, int* dNumNeighbors,
+                                           int* dOverflow, void* stream) {
+    MC_REQUIRE(radius > 0.0f, "mc_find_neighbors: radius must be positive");
+    MC_REQUIRE(window > 0.0f, "mc_find_neighbors_pdf_fused: window must be positive");
+    MC_REQUIRE(numCells > 0, "mc_find_neighbors: cell count must be positive");
+    MC_REQUIRE(dNumNeighbors != nullptr && pdfs != nullptr, "mc_find_neighbors_pdf_fused: outputs required");
+    MC_REQUIRE(((uintptr_t)workspace) % 8 == 0, "mc_find_neighbors_pdf_fused: workspace must be 8-byte aligned");
+    // One launch while the call is latency-bound; past kPdfFuseMaxSamples the per-sample density loop (one lane per
+    // pair of ONE sample: ~6 of 32 lanes busy on the up-sampling lists) costs more than the launch it saves
+    // (profiles/r2_neighbors_pdf_fused.txt), so the densities go to the pair-per-thread kernel of pdf.cu.
+    if (numSamples <= pdf_fuse_max_samples())
+        return launch_fused(scaleInv, numSamples, dNumSamples, numCells, radius, samples, sampleBatchIds, pts2,
+                            cellIdx, aabbMin, aabbMax, startIdx, workspace, pairs, capacityPairs, dNumNeighbors,
+                            dOverflow, window, pdfs, stream, "mc_find_neighbors_pdf_fused");
+    int rc = launch_fused(scaleInv, numSamples, dNumSamples, numCells, radius, samples, sampleBatchIds, pts2, cellIdx,
+                          aabbMin, aabbMax, startIdx, workspace, pairs, capacityPairs, dNumNeighbors, dOverflow, 0.f,
+                          nullptr, stream, "mc_find_neighbors_pdf_fused");
+    if (rc != 0) return rc;
+    return launch_pdf_by_sample(scaleInv != 0, window, radius, dNumSamples, numSamples, dNumNeighbors, capacityPairs,
+                                pts2, sampleBatchIds, aabbMin, aabbMax, startIdx, pairs, pdfs, (cudaStream_t)stream);
 }
 
 // countNeighborsCPU, tf_ops/find_neighbors.cu:268-317 -- without the cudaMalloc / D2H: the total lands in

@@ -16,12 +16,8 @@ namespace {
 constexpr int kPdfThreads = 256;
 constexpr int kPdfStage = 2048;  // staged neighbour coordinates per CTA (24 KB)
 
-__device__ __forceinline__ float ex2_approx(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-
+// BY_SAMPLE: bids holds the SAMPLES' batch ids (a neighbour lies in its sample's cloud), else the points'.
+template <bool BY_SAMPLE>
 __global__ void __launch_bounds__(kPdfThreads)
     pdf_kernel(bool scaleInv, float window, float radius, const int* __restrict__ dM, int capM,
                const int* __restrict__ dK, int capK, const float* __restrict__ pts, const int* __restrict__ bids,
@@ -50,33 +46,41 @@ __global__ void __launch_bounds__(kPdfThreads)
     if (p >= K) return;
     const int2 pr = pairs[p];
     const int j = pr.x, i = pr.y;
-    const float ext = max_extent(mn, mx, bids[j]);
+    const float ext = max_extent(mn, mx, bids[BY_SAMPLE ? i : j]);
     const float r = scaleInv ? radius * ext : radius;
     const int lo = start[i];
     const int hi = min((i < M - 1) ? start[i + 1] : K, K);
-    const float invH = 1.0f / window;
-    const float invRadH = 1.0f / (r * window);
-    // exp(-0.5 * |d|^2 * invRadH^2) = 2^(|d|^2 * e2)
-    const float e2 = -0.72134752044448170368f * invRadH * invRadH;
+    // exp(-0.5 * |d|^2 / (r h)^2) = 2^(|d|^2 * e2)
+    const float e2 = pdf_exponent_scale(r, window);
     const float xj = pts[(size_t)j * 3], yj = pts[(size_t)j * 3 + 1], zj = pts[(size_t)j * 3 + 2];
     float acc = 0.0f;
     int q = lo;
     const int qStagedEnd = min(hi, wLo + staged);
     for (; q < qStagedEnd; ++q) {
         int t = q - wLo;
-        float dx = sx[t] - xj, dy = sy[t] - yj, dz = sz[t] - zj;
-        acc += ex2_approx((dx * dx + dy * dy + dz * dz) * e2);
+        acc += pdf_term(sx[t] - xj, sy[t] - yj, sz[t] - zj, e2);
     }
     for (; q < hi; ++q) {  // neighbour list longer than the stage: read through L1/L2
         int jj = pairs[q].x;
-        float dx = pts[(size_t)jj * 3] - xj, dy = pts[(size_t)jj * 3 + 1] - yj, dz = pts[(size_t)jj * 3 + 2] - zj;
-        acc += ex2_approx((dx * dx + dy * dy + dz * dz) * e2);
+        acc += pdf_term(pts[(size_t)jj * 3] - xj, pts[(size_t)jj * 3 + 1] - yj, pts[(size_t)jj * 3 + 2] - zj, e2);
     }
-    const float g = invH * 0.39894228f;
-    pdf[p] = (acc * (g * g * g)) / (float)(hi - lo);
+    pdf[p] = pdf_finish(acc, window, hi - lo);
 }
 
 }  // namespace
+
+// mc_compute_pdf for a pair list just produced by the fused neighbour kernel (neighbors.cu), which has the samples'
+// batch ids at hand, not the points'.
+int launch_pdf_by_sample(bool scaleInv, float window, float radius, const int* dM, int capM, const int* dK, int capK,
+                         const float* pts, const int* sampleBids, const float* mn, const float* mx, const int* start,
+                         const int* pairs, float* pdf, cudaStream_t s) {
+    if (capK <= 0) return 0;
+    pdf_kernel<true><<<cdiv(capK, kPdfThreads), kPdfThreads, 0, s>>>(scaleInv, window, radius, dM, capM, dK, capK, pts,
+                                                                      sampleBids, mn, mx, start,
+                                                                      reinterpret_cast<const int2*>(pairs), pdf);
+    return check_launch("mc_find_neighbors_pdf_fused (densities)");
+}
+
 }  // namespace mc
 
 using namespace mc;
@@ -88,7 +92,7 @@ extern "C" int mc_compute_pdf(int scaleInv, float window, int numSamples, const 
     MC_REQUIRE(window > 0.0f, "mc_compute_pdf: window must be positive");
     MC_REQUIRE(radius > 0.0f, "mc_compute_pdf: radius must be positive");
     if (numNeighbors <= 0) return 0;
-    pdf_kernel<<<cdiv(numNeighbors, kPdfThreads), kPdfThreads, 0, (cudaStream_t)stream>>>(
+    pdf_kernel<false><<<cdiv(numNeighbors, kPdfThreads), kPdfThreads, 0, (cudaStream_t)stream>>>(
         scaleInv != 0, window, radius, dNumSamples, numSamples, dNumNeighbors, numNeighbors, pts, batchIds, aabbMin,
         aabbMax, startIdx, reinterpret_cast<const int2*>(pairs), pdfs);
     return check_launch("mc_compute_pdf");

@@ -200,6 +200,24 @@ def find_neighbors_fused(samples, sbids, pts2, cell_idx, aabb_min, aabb_max, rad
     return start, pairs, k_dev
 
 
+def find_neighbors_pdf_fused(samples, sbids, pts2, cell_idx, aabb_min, aabb_max, radius, window, scale_inv, capacity,
+                             m_dev=None, overflow=None):
+    """find_neighbors_fused + compute_pdf in one launch.  Returns (start[M], pairs[capacity, 2], pdf[capacity], k_dev)."""
+    samples, sbids, pts2, cell_idx = _f(samples), _i(sbids), _f(pts2), _i(cell_idx)
+    dev = _dev(samples)
+    M = samples.shape[0]
+    start = torch.empty((M,), dtype=_i32, device=dev)
+    pairs = torch.empty((capacity, 2), dtype=_i32, device=dev)
+    pdf = torch.empty((capacity,), dtype=_f32, device=dev)
+    k_dev = torch.empty((1,), dtype=_i32, device=dev)
+    ws = torch.empty((lib.mc_find_neighbors_workspace_ints(M),), dtype=_i32, device=dev)
+    check(lib.mc_find_neighbors_pdf_fused(int(scale_inv), float(window), M, _p(m_dev), cell_idx.shape[1], float(radius),
+                                          _p(samples), _p(sbids), _p(pts2), _p(cell_idx), _p(aabb_min), _p(aabb_max),
+                                          _p(start), _p(ws), _p(pairs), _p(pdf), capacity, _p(k_dev), _p(overflow),
+                                          _stream()))
+    return start, pairs, pdf, k_dev
+
+
 def compute_pdf(pts, bids, aabb_min, aabb_max, start, pairs, window, radius, scale_inv, m_dev=None, k_dev=None):
     pts, bids, start, pairs = _f(pts), _i(bids), _i(start), _i(pairs)
     dev = _dev(pts)

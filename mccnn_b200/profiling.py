@@ -52,6 +52,9 @@ ALGORITHMIC_BYTES = {
     "find_neighbors_fused": lambda a, kw, r, B: (16 * _live(a[0]) + 12 * _live(a[2]) +
                                                  8 * min(_cells(a[3]), 27 * _live(a[0])) + 4 * _live(a[0]) +
                                                  8 * _count(r[2])),
+    "find_neighbors_pdf_fused": lambda a, kw, r, B: (16 * _live(a[0]) + 12 * _live(a[2]) +
+                                                     8 * min(_cells(a[3]), 27 * _live(a[0])) + 4 * _live(a[0]) +
+                                                     12 * _count(r[3]) + 12 * _live(a[2])),
     "find_neighbors_count": lambda a, kw, r, B: (16 * _live(a[0]) + 12 * _live(a[2]) +
                                                  8 * min(_cells(a[3]), 27 * _live(a[0])) + 4 * _live(a[0])),
     "find_neighbors_pack": lambda a, kw, r, B: (16 * _live(a[0]) + 12 * _live(a[2]) +

@@ -73,6 +73,31 @@ def test_mcclasss_exact_planned_graph_identical(B, N, k):
     assert close(out2, ref2)
 
 
+def test_fused_neighbors_pdf_builder_path_is_bit_identical(monkeypatch):
+    """MCCNN_FUSE_PDF=1 (one launch for find_neighbors + compute_pdf of a new neighbour list in planned mode) changes
+    how the forward is issued, not one bit of its result."""
+    import torch
+    from mccnn_b200 import MCConvBuilder, ops
+    from mccnn_b200.engine import PlannedForward
+    dev = torch.device("cuda:0")
+    B = 8
+    fn, store = _make(B, 32, 40, dev)
+    pts, bids, feats = make_batch(B, 1024, "sphere", seed=21)
+    tp, tb, tf = (torch.from_numpy(a).to(dev) for a in (pts, bids, feats))
+    fn(tp, tb, tf)
+    _randomize_store(store)
+    ref = fn(tp, tb, tf)[:B].clone()
+    monkeypatch.setattr(MCConvBuilder, "FUSE_NEIGHBORS_PDF", True)
+    calls = []
+    orig = ops.find_neighbors_pdf_fused
+    monkeypatch.setattr(ops, "find_neighbors_pdf_fused", lambda *a, **kw: (calls.append(1), orig(*a, **kw))[1])
+    eng = PlannedForward(fn, B, use_graph=True)
+    assert torch.equal(eng(tp, tb, tf), ref)          # records (exact ops)
+    assert torch.equal(eng(tp, tb, tf), ref)          # planned: captures the fused launches
+    assert torch.equal(eng(tp, tb, tf), ref)          # replay
+    assert len(calls) == 3                            # MCClassS builds three neighbour lists with densities
+
+
 def test_planned_ops_bit_identical():
     """Hierarchy + Conv_1 (no dense glue in between): planned, capacity-padded results equal the exact ones bit for
     bit on their live rows, for every tensor the builder exposes."""

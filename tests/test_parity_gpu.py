@@ -137,6 +137,37 @@ def test_find_neighbors_fused_bit_exact(env, B, N, dist, ragged, radius, scaleIn
             assert int(flag.item()) == 1
 
 
+@pytest.mark.parametrize("B,N,dist,ragged,radius,scaleInv", CASES + [(4, 4000, "sphere", False, 0.03, True),
+                                                                      (2, 20000, "room", False, 0.1, False),
+                                                                      (1, 3000, "cube", False, 0.6, False),
+                                                                      (8, 4096, "sphere", False, 0.1, False)])
+def test_find_neighbors_pdf_fused_equals_the_two_ops(env, B, N, dist, ragged, radius, scaleInv):
+    """mc_find_neighbors_pdf_fused (neighbour list + densities in one launch) == mc_find_neighbors_fused followed by
+    mc_compute_pdf: same start indices and pairs, and the SAME float for every density (same terms in the same order),
+    including neighbour lists longer than the kernel's per-warp coordinate stage (the radius-0.6 case) and calls above
+    the sample count at which the entry point hands the densities to the pair-per-thread kernel (8 x 4096)."""
+    e = env
+    O, T, A, torch = e["O"], e["T"], e["A"], e["torch"]
+    from mccnn_b200 import ops
+    pts, bids, feats = make_batch(B, N, dist, seed=14, num_features=1, ragged=ragged)
+    mn, mx, keys, idx, sp, sb, sf, cells = _grid(e, pts, bids, feats, B, radius, scaleInv, O)
+    smp, smpb, _ = O.poisson_sampling(sp, sb, cells, mn, mx, radius * 0.5, B, scaleInv)
+    for samples, sbids in ((smp, smpb), (sp, sb)):
+        ostart, opairs = O.find_neighbors(samples, sbids, sp, cells, mn, mx, radius, B, scaleInv)
+        K = opairs.shape[0]
+        flag = torch.zeros((1,), dtype=torch.int32, device=e["dev"])
+        geo = (T(samples), T(sbids).reshape(-1), T(sp), T(cells), T(mn), T(mx))
+        start, pairs, pdf, k_dev = ops.find_neighbors_pdf_fused(*geo, radius, 0.25, scaleInv, K + 64, overflow=flag)
+        assert int(k_dev.item()) == K and int(flag.item()) == 0
+        assert np.array_equal(A(start), ostart.reshape(-1))
+        assert np.array_equal(A(pairs)[:K], opairs)
+        want = ops.compute_pdf(T(sp), T(sb).reshape(-1), T(mn), T(mx), start, pairs[:K].contiguous(), 0.25, radius,
+                               scaleInv)
+        assert torch.equal(pdf[:K], want.reshape(-1))
+        opdf = O.compute_pdf(sp, sb, mn, mx, ostart, opairs, 0.25, radius, B, scaleInv)
+        np.testing.assert_allclose(A(pdf)[:K], opdf.reshape(-1), rtol=1e-5, atol=1e-7)
+
+
 @pytest.mark.parametrize("B,N,dist,ragged,radius,scaleInv", CASES)
 def test_poisson_bit_exact(env, B, N, dist, ragged, radius, scaleInv):
     e = env

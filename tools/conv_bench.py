@@ -41,7 +41,7 @@ def main():
         calls.append((a, kw))
         return orig(*a, **kw)
     setattr(ops, args.op, rec)
-    if args.op in ("find_neighbors_fused",):   # only issued by the planned (sync-free) path
+    if args.op in ("find_neighbors_fused", "find_neighbors_pdf_fused"):   # only issued by the planned (sync-free) path
         from mccnn_b200.engine import PlannedForward
         eng = PlannedForward(lambda p, b, f: mod.create_network(p, b, f, *lead[3:], *bench.net_args(w, w["B"], "ours"),
                                                                 store=store),
@@ -57,6 +57,7 @@ def main():
     flush = torch.zeros(192 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
     peak = bench.measured_peaks()[0]
     total = 0.0
+    total2 = 0.0
     print("%s %d x %d: %d %s calls" % (w["model"], w["B"], w["P"], len(calls), args.op))
     for n, (a, kw) in enumerate(calls):
         if args.once:
@@ -85,6 +86,35 @@ def main():
                   "peak) | %6.2f G pair-blocks/s | %5.1f TFLOP/s useful" %
                   (n, N, M, K, K / max(M, 1), C, nout, nb, med, by / med * 1e-3, by / med * 1e-3 / peak,
                    K * nb / med * 1e-3, K * nb * 320 / med * 1e-6))
+        elif args.op == "find_neighbors_pdf_fused":
+            # the pair it replaces, on the same inputs: mc_find_neighbors_fused, then mc_compute_pdf on its result
+            smp, sb, p2, cidx, mn, mx, rad, win, sinv, cap = a[:10]
+            b2 = torch.zeros((p2.shape[0],), dtype=torch.int32, device=dev)
+            # batch ids of the sorted points: cloud of the cell range they fall in is not needed for fixed radii;
+            # with relative radii take them from the samples' neighbours
+            out = orig(*a, **kw)
+            k = int(out[3].item())
+            if sinv:
+                b2[out[1][:k, 0].long()] = sb[out[1][:k, 1].long()]
+
+            def pair():
+                st, pr, kd = ops.find_neighbors_fused(smp, sb, p2, cidx, mn, mx, rad, sinv, cap, *a[10:], **kw)
+                return ops.compute_pdf(p2, b2, mn, mx, st, pr, win, rad, sinv, a[10] if len(a) > 10 else kw.get("m_dev"),
+                                       kd)
+            pair()
+            us2 = []
+            for _ in range(args.reps):
+                flush.add_(1.0)
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                pair()
+                e.record()
+                torch.cuda.synchronize()
+                us2.append(s.elapsed_time(e) * 1e3)
+            med2 = float(np.median(us2))
+            total2 += med2
+            print("  #%2d samples=%7d points=%7d pairs=%8d (%5.1f / sample) | fused %8.1f us | neighbours + pdf %8.1f us "
+                  "| %.2fx" % (n, smp.shape[0], p2.shape[0], k, k / max(smp.shape[0], 1), med, med2, med2 / med))
         elif args.op.startswith("find_neighbors"):
             out = orig(*a, **kw)
             k = int(out[2].item()) if len(out) > 2 else -1
@@ -105,6 +135,8 @@ def main():
                    2.0 * x.shape[0] * wgt.shape[0] * wgt.shape[1] / med * 1e-6))
     if not args.once:
         print("  total %.1f us" % total)
+        if total2 > 0:
+            print("  total of the two separate launches %.1f us -> %.2fx" % (total2, total2 / total))
 
 
 if __name__ == "__main__":

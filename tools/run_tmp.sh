@@ -1,2 +1,10 @@
-timeout 600 python -m pytest tests/test_parity_gpu.py tests/test_model_gpu.py tests/test_models_gpu.py -x -q -k "neighbors or planned or model or Model" 2>&1 | tail -4
-for c in 5 4 2; do timeout 300 python tools/conv_bench.py --config $c --op find_neighbors_fused --reps 10 2>&1 | tail -16 | cut -c1-140; done
+#!/bin/bash
+mkdir -p gpurun_out/r2m
+for rep in 1 2 3; do
+for v in 0 8192 600; do
+  echo "MCCNN_PDF_FUSE_MAX=$v"
+  MCCNN_PDF_FUSE_MAX=$v timeout 600 python bench.py --no-other-configs 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.readline()); print(d['value'], d['ms_per_step'], d['latency']['ms_per_forward'], d['e2e']['value'])"
+done
+done
