@@ -24,6 +24,8 @@
 #include "lookback.cuh"
 
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 
 namespace mc {
 namespace {
@@ -31,6 +33,8 @@ namespace {
 constexpr int kSelThreads = 512;
 constexpr int kSelWarps = kSelThreads / 32;
 constexpr int kSelFlagBytes = 48 * 1024;  // per-cloud accepted flags kept in shared memory up to this many points
+// (these four are the LARGEST capacities; a launch carves its shared memory for the capacities its batch needs --
+// SelCaps -- so that the CTAs of a small level leave room for other kernels' CTAs on the same SM)
 constexpr int kListCap = 128;             // accepted neighbour candidates a warp keeps in shared memory
 constexpr int kSelfOffset = 17;           // index of (0,0,0) in kOffsPool
 constexpr int kCellListCap = 8192;        // cells per cloud up to which the per-phase non-empty cell lists are built
@@ -79,6 +83,15 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
         "r"(parity)
         : "memory");
 }
+
+// shared-memory capacities of one launch (all multiples of 16); a cloud above one of them takes the corresponding
+// global-memory path, exactly as a cloud above the largest capacities does
+struct SelCaps {
+    int flagBytes;   // accepted flags in shared memory up to this many points per cloud
+    int cellList;    // per-phase non-empty cell lists up to this many cells per cloud
+    int stageCells;  // cell-table rows staged up to this many cells per cloud
+    int stagePts;    // points staged up to this many points per cloud
+};
 
 struct SelShared {
     float4 list[kSelWarps][kListCap];
@@ -259,17 +272,17 @@ __global__ void __launch_bounds__(kSelThreads)
                    const float* __restrict__ mx, const float* __restrict__ pts, const int2* __restrict__ cellIdx,
                    unsigned char* selGlobal, int* __restrict__ tmpIdx, unsigned long long* chain, int capOut,
                    float* __restrict__ outPts, int* __restrict__ outBids, int* __restrict__ outIdx,
-                   int* __restrict__ dNumSamples, int* __restrict__ dOverflow, bool phasesDone) {
+                   int* __restrict__ dNumSamples, int* __restrict__ dOverflow, bool phasesDone, SelCaps caps) {
     // phasesDone: the accepted flags were already produced in selGlobal by the many-CTA phase kernels (fine grids);
     // this launch then only orders and writes the samples
     extern __shared__ __align__(16) unsigned char smemRaw[];
     SelShared& sh = *reinterpret_cast<SelShared*>(smemRaw);
     unsigned char* sFlags = smemRaw + sizeof(SelShared);
-    unsigned short* cellList = reinterpret_cast<unsigned short*>(sFlags + kSelFlagBytes);
-    int2* sCells = reinterpret_cast<int2*>(sFlags + kSelFlagBytes + kCellListCap * sizeof(unsigned short));
-    float* sPts = reinterpret_cast<float*>(sCells + kStageCells);  // + 16 bytes of slack for the alignment shift
-    unsigned short* sAccIdx = reinterpret_cast<unsigned short*>(sPts + kStagePts * 3 + 4);
-    unsigned char* sAccCnt = reinterpret_cast<unsigned char*>(sAccIdx + kStagePts);
+    unsigned short* cellList = reinterpret_cast<unsigned short*>(sFlags + caps.flagBytes);
+    int2* sCells = reinterpret_cast<int2*>(sFlags + caps.flagBytes + caps.cellList * sizeof(unsigned short));
+    float* sPts = reinterpret_cast<float*>(sCells + caps.stageCells);  // + 16 bytes of slack for the alignment shift
+    unsigned short* sAccIdx = reinterpret_cast<unsigned short*>(sPts + caps.stagePts * 3 + 4);
+    unsigned char* sAccCnt = reinterpret_cast<unsigned char*>(sAccIdx + caps.stagePts);
     const int lane = lane_id(), warp = threadIdx.x >> 5;
     const unsigned ltMask = (1u << lane) - 1u;
 
@@ -290,8 +303,8 @@ __global__ void __launch_bounds__(kSelThreads)
     const int b = sh.cloud;
     const int cellsPerCloud = n * n * n;
     const int2* cells = cellIdx + (size_t)b * cellsPerCloud;
-    const bool useLists = cellsPerCloud <= kCellListCap && !phasesDone;
-    const bool stageCells = cellsPerCloud <= kStageCells && !phasesDone;
+    const bool useLists = cellsPerCloud <= caps.cellList && !phasesDone;
+    const bool stageCells = cellsPerCloud <= caps.stageCells && !phasesDone;
 
     // extent of this cloud inside the sorted array (the sort is batch-major) + non-empty cells per phase
     {
@@ -322,12 +335,12 @@ __global__ void __launch_bounds__(kSelThreads)
     __syncthreads();
     const int cLo = sh.lo, cHi = sh.hi;
     const int nCloud = cHi > cLo ? cHi - cLo : 0;
-    const bool inSmem = nCloud <= kSelFlagBytes && !phasesDone;
+    const bool inSmem = nCloud <= caps.flagBytes && !phasesDone;
     if (inSmem)
         for (int t = threadIdx.x; t < nCloud; t += kSelThreads) sFlags[t] = 0;
     // every later access to the cloud's points and cell rows is then a shared-memory access: the per-cell work is a
     // chain of dependent loads, and first-touch global misses were what made it slow
-    const bool stagePts = nCloud <= kStagePts && !phasesDone;
+    const bool stagePts = nCloud <= caps.stagePts && !phasesDone;
     if (stagePts) {
         // the cloud's points are one contiguous range of 12-byte rows: the 16-byte aligned interior goes through ONE
         // TMA bulk copy, the (at most 12 + 12) bytes before / after it through plain loads; the shared-memory image
@@ -563,9 +576,32 @@ __global__ void __launch_bounds__(kSelThreads)
     }
 }
 
-constexpr size_t kSelSmemBytes = sizeof(SelShared) + kSelFlagBytes + kCellListCap * sizeof(unsigned short) +
-                                 kStageCells * sizeof(int2) + (kStagePts * 3 + 4) * sizeof(float) +
-                                 kStagePts * sizeof(unsigned short) + kStageCells;
+constexpr size_t sel_smem_bytes(const SelCaps& c) {
+    return sizeof(SelShared) + c.flagBytes + c.cellList * sizeof(unsigned short) + c.stageCells * sizeof(int2) +
+           (c.stagePts * 3 + 4) * sizeof(float) + c.stagePts * sizeof(unsigned short) + c.stageCells;
+}
+constexpr SelCaps kSelMaxCaps = {kSelFlagBytes, kCellListCap, kStageCells, kStagePts};
+constexpr size_t kSelSmemBytes = sel_smem_bytes(kSelMaxCaps);
+constexpr int round16(long long v) { return (int)((v + 15) / 16 * 16); }
+
+// Capacities for a batch of numPoints points in batchSize clouds on an n^3 grid: the cell structures are sized
+// exactly; points are staged up to twice the mean cloud (ragged batches: a larger cloud reads its points through
+// L1 / L2 instead) and flags up to eight times.  MCCNN_POISSON_STAGE=full asks for the largest capacities always.
+SelCaps choose_caps(long long numPoints, int batchSize, long long cellsPerCloud, bool phasesDone) {
+    static const bool full = [] {
+        const char* e = getenv("MCCNN_POISSON_STAGE");
+        return e != nullptr && strcmp(e, "full") == 0;
+    }();
+    if (phasesDone) return SelCaps{0, 0, 0, 0};  // the ordering pass of the fine-grid path stages nothing
+    if (full) return kSelMaxCaps;
+    const long long mean = (numPoints + batchSize - 1) / batchSize;
+    SelCaps c;
+    c.stagePts = round16(std::min<long long>(kStagePts, std::max<long long>(256, 2 * mean)));
+    c.flagBytes = round16(std::min<long long>(kSelFlagBytes, std::max<long long>(c.stagePts, std::min(numPoints, 8 * mean))));
+    c.cellList = cellsPerCloud <= kCellListCap ? round16(cellsPerCloud) : 0;
+    c.stageCells = cellsPerCloud <= kStageCells ? round16(cellsPerCloud) : 0;
+    return c;
+}
 
 }  // namespace
 }  // namespace mc
@@ -627,9 +663,10 @@ extern "C" int mc_poisson_sampling(int scaleInv, float radius, int numPoints, co
         count_launches(29);
     }
     if (numPoints > 0) {
-        poisson_kernel<<<batchSize, kSelThreads, kSelSmemBytes, s>>>(
+        const SelCaps caps = choose_caps(numPoints, batchSize, cellsPerCloud, fineGrid);
+        poisson_kernel<<<batchSize, kSelThreads, sel_smem_bytes(caps), s>>>(
             scaleInv != 0, radius, batchSize, numCells, aabbMin, aabbMax, pts, reinterpret_cast<const int2*>(cellIdx),
-            sel, tmpIdx, chain, capacityOut, outPts, outBatchIds, outIdx, dNumSamples, dOverflow, fineGrid);
+            sel, tmpIdx, chain, capacityOut, outPts, outBatchIds, outIdx, dNumSamples, dOverflow, fineGrid, caps);
     } else {
         cudaMemsetAsync(dNumSamples, 0, sizeof(int), s);
     }

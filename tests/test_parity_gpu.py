@@ -10,7 +10,7 @@ launch) the comparison is on the canonicalised form -- see oracle/mccnn_oracle.c
 import numpy as np
 import pytest
 
-from common import make_batch, make_conv_weights, rel_err, sum_err
+from common import make_batch, make_cloud, make_conv_weights, rel_err, sum_err
 
 pytestmark = pytest.mark.gpu
 
@@ -194,6 +194,27 @@ def test_poisson_bit_exact(env, B, N, dist, ragged, radius, scaleInv):
         group = np.array([rb[k] * 27 + phase_of[int(ri[k])] for k in range(ri.shape[0])])
         assert np.all(np.diff(group) >= 0)
         assert np.array_equal(A(rp), sp[ri])
+
+
+@pytest.mark.parametrize("sizes,radius", [((3000, 100, 100, 100), 0.1),       # one cloud above the staged-points capacity
+                                          ((6000,) + (50,) * 11, 0.08),        # ... and above the shared-memory flags
+                                          ((40, 5000, 40, 0, 700, 40), 0.12)])  # empty cloud in the middle
+def test_poisson_bit_exact_on_very_ragged_batches(env, sizes, radius):
+    """poisson_kernel sizes its shared-memory staging for twice the MEAN cloud of the batch (choose_caps); a cloud far
+    above the mean takes the global-memory paths of the same kernel and must give the same samples."""
+    e = env
+    O, M, T, A = e["O"], e["M"], e["T"], e["A"]
+    B = len(sizes)
+    pts = np.concatenate([make_cloud(n, "sphere", np.random.default_rng(70 + b)).reshape(-1, 3)
+                          for b, n in enumerate(sizes)]).astype(np.float32)
+    bids = np.concatenate([np.full((n, 1), b, np.int32) for b, n in enumerate(sizes)])
+    feats = np.ones((pts.shape[0], 1), np.float32)
+    mn, mx, keys, idx, sp, sb, sf, cells = _grid(e, pts, bids, feats, B, radius, False, O)
+    op, ob, oi = O.poisson_sampling(sp, sb, cells, mn, mx, radius, B, False)
+    gp, gb, gi = M.poisson_sampling(T(sp), T(sb), T(cells), T(mn), T(mx), radius, B, False)
+    assert np.array_equal(A(gi), oi)
+    assert np.array_equal(A(gb), ob)
+    assert np.array_equal(A(gp), op)
 
 
 PDF_CASES = [(1, 1024, "cube", 0.1, 0.2, True), (1, 1024, "sphere", 0.1, 0.2, True),
