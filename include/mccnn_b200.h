@@ -201,6 +201,15 @@ int mc_mlp_rows(int numRows, const int* dNumRows, int numLayers, const int* dims
                 const float* t0, int relu0, const float* const* W, const float* const* bias,
                 const float* const* scale, const float* const* shift, const int* relu, float* y, void* stream);
 
+/* mc_dense_layer for FEW live rows (one per cloud: the classification heads, MLP_1_hidden / MLP_2_hidden,
+ * utils/MCNetworkUtils.py:20-107) and layers of any width -- MCClassH's 2048 -> 1024 -> 512 head.  Every CTA owns
+ * (128 columns) x (a K segment) for all rows, so W is read once; the K segments are summed in a fixed order
+ * (deterministic).  numRows is the capacity of x / y; workspace: mc_dense_fewrows_workspace_floats floats (may be 0). */
+long long mc_dense_fewrows_workspace_floats(int numRows, int K, int N);
+int mc_dense_layer_fewrows(int numRows, const int* dNumRows, int K, int N, const float* x, const float* s1,
+                           const float* t1, int relu1, const float* W, const float* bias, const float* s2,
+                           const float* t2, int relu2, float* workspace, float* y, void* stream);
+
 /* ---- dense glue on the tcgen05 tensor cores (csrc/dense_tc.cu): the same layer as mc_dense_layer for many rows,
  * FP32 in / FP32 out through the 3xTF32 split, TMA-fed, accumulator in TMEM.  Replaces tf.matmul (cuBLAS) + the
  * TensorFlow batch-norm / ReLU ops around it (utils/MCNetworkUtils.py:109-142).  The static operand is the weight

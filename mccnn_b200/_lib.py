@@ -61,6 +61,9 @@ SIGNATURES = {
     "mc_mlp_rows": (_c_int, [_c_int, _ptr, _c_int, _ptr, _ptr, _ptr, _ptr, _c_int, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr,
                              _ptr]),
     "mc_split_tf32": (_c_int, [_c_ll, _ptr, _ptr, _ptr, _ptr]),
+    "mc_dense_fewrows_workspace_floats": (_c_ll, [_c_int, _c_int, _c_int]),
+    "mc_dense_layer_fewrows": (_c_int, [_c_int, _ptr, _c_int, _c_int, _ptr, _ptr, _ptr, _c_int, _ptr, _ptr, _ptr, _ptr, _c_int,
+                                        _ptr, _ptr, _ptr]),
     "mc_dense_layer_tc_supported": (_c_int, [_c_int, _c_int]),
     "mc_dense_layer_tc": (_c_int, [_c_int, _ptr, _c_int, _c_int, _ptr, _ptr, _ptr, _c_int, _ptr, _ptr, _ptr, _ptr, _ptr,
                                    _c_int, _ptr, _ptr]),

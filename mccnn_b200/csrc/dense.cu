@@ -14,6 +14,8 @@
 //     with the next chunk prefetched into registers while the current one is multiplied.
 #include "common.cuh"
 
+#include <algorithm>
+
 namespace mc {
 namespace {
 
@@ -208,10 +210,153 @@ __global__ void __launch_bounds__(kDnThreads)
     }
 }
 
+// ---- few rows, wide layers (the 2048 -> 1024 -> 512 classification heads of MCClassH: 32 rows) ---------------------
+// Such a layer is a stream of W through the GPU: 8 MB of weights against 32 x 2048 inputs.  One CTA per row (above)
+// reads W once PER ROW and has 32 CTAs in flight; here every CTA owns (128 columns) x (a K segment) for ALL rows of a
+// 32-row group -- a thread is one column with 32 accumulators, the activated input segment sits in shared memory
+// transposed ([k][row], read as broadcast float4) -- so W crosses the memory system once and the (column slice, K
+// segment) grid covers the GPU twice over.  The K segments are summed in a FIXED order by a second small launch
+// (deterministic: no atomics), which also applies the epilogue; a layer small enough for one segment needs only the
+// first launch.
+constexpr int kFrCols = 128, kFrRows = 32, kFrMaxKS = 128, kFrStride = kFrRows + 4;  // segLen: multiple of 8
+
+struct FewRowsPlan {
+    int slices, segments, segLen;
+};
+FewRowsPlan fewrows_plan(int K, int N) {
+    FewRowsPlan p;
+    p.slices = cdiv(N, kFrCols);
+    int S = (long long)K * N < (1 << 15) ? 1 : std::max(1, std::min(cdiv(2 * 148, p.slices), cdiv(K, 32)));
+    p.segLen = std::min(kFrMaxKS, (cdiv(K, S) + 7) / 8 * 8);
+    p.segments = cdiv(K, p.segLen);
+    return p;
+}
+
+template <bool DIRECT>
+__global__ void __launch_bounds__(kFrCols)
+    dense_fewrows_kernel(const int* __restrict__ dRows, int capRows, int K, int N, int segLen,
+                         const float* __restrict__ x, const float* __restrict__ s1, const float* __restrict__ t1,
+                         int relu1, const float* __restrict__ W, const float* __restrict__ bias,
+                         const float* __restrict__ s2, const float* __restrict__ t2, int relu2,
+                         float* __restrict__ out) {
+    __shared__ __align__(16) float xs[kFrMaxKS][kFrStride];
+    const int r0 = blockIdx.z * kFrRows;
+    const int k0 = blockIdx.y * segLen, kLen = min(segLen, K - k0);
+    const int col = blockIdx.x * kFrCols + threadIdx.x;
+    const bool active = col < N;
+    // weights: chunks of 8 rows of W per thread, the next chunk's loads issued before this chunk's FMAs (the layer is
+    // a stream of W out of HBM: what matters is bytes in flight); the first chunk is requested before the inputs are
+    // staged; rows past the segment read as zero
+    const float* w = W + (size_t)k0 * N + (active ? col : 0);
+    constexpr int kChunk = 8;
+    float cur[kChunk], nxt[kChunk];
+#pragma unroll
+    for (int u = 0; u < kChunk; ++u) cur[u] = (active && u < kLen) ? __ldg(w + (size_t)u * N) : 0.0f;
+    const int rows = live_count(dRows, capRows);
+    if (r0 >= rows) return;
+    // activated input segment, transposed; rows past the live count are zero
+    for (int e = threadIdx.x; e < kFrRows * segLen; e += kFrCols) {
+        const int r = e / segLen, kk = e - r * segLen;
+        float v = 0.0f;
+        if (r0 + r < rows && kk < kLen) {
+            v = x[(size_t)(r0 + r) * K + k0 + kk];
+            if (s1 != nullptr) v = fmaf(v, s1[k0 + kk], t1[k0 + kk]);
+            if (relu1) v = fmaxf(v, 0.0f);
+        }
+        xs[kk][r] = v;
+    }
+    __syncthreads();
+    if (!active) return;
+    float acc[kFrRows];
+#pragma unroll
+    for (int r = 0; r < kFrRows; ++r) acc[r] = 0.0f;
+    for (int kk = 0; kk < kLen; kk += kChunk) {
+#pragma unroll
+        for (int u = 0; u < kChunk; ++u) {
+            const int k = kk + kChunk + u;
+            nxt[u] = k < kLen ? __ldg(w + (size_t)k * N) : 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < kChunk; ++u) {
+#pragma unroll
+            for (int r4 = 0; r4 < kFrRows / 4; ++r4) {
+                const float4 xv = *reinterpret_cast<const float4*>(&xs[kk + u][r4 * 4]);
+                acc[r4 * 4] = fmaf(xv.x, cur[u], acc[r4 * 4]);
+                acc[r4 * 4 + 1] = fmaf(xv.y, cur[u], acc[r4 * 4 + 1]);
+                acc[r4 * 4 + 2] = fmaf(xv.z, cur[u], acc[r4 * 4 + 2]);
+                acc[r4 * 4 + 3] = fmaf(xv.w, cur[u], acc[r4 * 4 + 3]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kChunk; ++u) cur[u] = nxt[u];
+    }
+    const int live = min(kFrRows, rows - r0);
+    if (DIRECT) {
+#pragma unroll
+        for (int r = 0; r < kFrRows; ++r)
+            if (r < live) out[(size_t)(r0 + r) * N + col] = epilogue(acc[r], col, bias, s2, t2, relu2);
+    } else {  // partial sums of this K segment: out[segment][row][column]
+        float* dst = out + ((size_t)blockIdx.y * capRows + r0) * N + col;
+#pragma unroll
+        for (int r = 0; r < kFrRows; ++r)
+            if (r < live) dst[(size_t)r * N] = acc[r];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+    dense_fewrows_reduce_kernel(const int* __restrict__ dRows, int capRows, int N, int segments,
+                                const float* __restrict__ partial, const float* __restrict__ bias,
+                                const float* __restrict__ s2, const float* __restrict__ t2, int relu2,
+                                float* __restrict__ y) {
+    const int rows = live_count(dRows, capRows);
+    const long long total = (long long)rows * N;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        float v = 0.0f;
+        for (int q = 0; q < segments; ++q) v += __ldcg(partial + (size_t)q * capRows * N + t);  // fixed order
+        y[t] = epilogue(v, (int)(t % N), bias, s2, t2, relu2);
+    }
+}
+
 }  // namespace
 }  // namespace mc
 
 using namespace mc;
+
+// floats of workspace mc_dense_layer_fewrows needs for a [numRows, K] x [K, N] layer (0: none)
+extern "C" long long mc_dense_fewrows_workspace_floats(int numRows, int K, int N) {
+    if (numRows <= 0 || K <= 0 || N <= 0) return 0;
+    const FewRowsPlan p = fewrows_plan(K, N);
+    return p.segments > 1 ? (long long)p.segments * numRows * N : 0;
+}
+
+// mc_dense_layer for FEW live rows (one per cloud: the classification heads, utils/MCNetworkUtils.py:20-107) and
+// layers of any width: same arithmetic contract, W read once for all rows.  numRows is the capacity of x / y;
+// workspace: mc_dense_fewrows_workspace_floats(numRows, K, N) floats.
+extern "C" int mc_dense_layer_fewrows(int numRows, const int* dNumRows, int K, int N, const float* x, const float* s1,
+                                      const float* t1, int relu1, const float* W, const float* bias, const float* s2,
+                                      const float* t2, int relu2, float* workspace, float* y, void* stream) {
+    MC_REQUIRE(K > 0 && N > 0, "mc_dense_layer_fewrows: layer sizes must be positive");
+    MC_REQUIRE((s1 == nullptr) == (t1 == nullptr) && (s2 == nullptr) == (t2 == nullptr),
+               "mc_dense_layer_fewrows: scale and shift come in pairs");
+    if (numRows <= 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    const FewRowsPlan p = fewrows_plan(K, N);
+    MC_REQUIRE(p.segments == 1 || workspace != nullptr, "mc_dense_layer_fewrows: workspace required");
+    const dim3 grid(p.slices, p.segments, cdiv(numRows, kFrRows));
+    if (p.segments == 1) {
+        dense_fewrows_kernel<true><<<grid, kFrCols, 0, s>>>(dNumRows, numRows, K, N, p.segLen, x, s1, t1, relu1, W, bias,
+                                                            s2, t2, relu2, y);
+        return check_launch("mc_dense_layer_fewrows");
+    }
+    dense_fewrows_kernel<false><<<grid, kFrCols, 0, s>>>(dNumRows, numRows, K, N, p.segLen, x, s1, t1, relu1, W, bias, s2,
+                                                         t2, relu2, workspace);
+    const int rgrid = std::max(1, std::min(cdiv((long long)numRows * N, 256), 148 * 4));
+    dense_fewrows_reduce_kernel<<<rgrid, 256, 0, s>>>(dNumRows, numRows, N, p.segments, workspace, bias, s2, t2, relu2,
+                                                      y);
+    count_launches(1);
+    return check_launch("mc_dense_layer_fewrows");
+}
 
 // y[r, c] = act(x[r, c] * scale[c] + shift[c]) for the live rows -- inference batch norm (+ ReLU),
 // utils/MCNetworkUtils.py:128-142 with the four statistics folded into (scale, shift) by the caller.

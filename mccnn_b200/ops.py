@@ -333,6 +333,23 @@ def dense_layer(x, w, bias=None, pre=None, pre_relu=False, post=None, post_relu=
     return y
 
 
+def dense_layer_fewrows(x, w, bias=None, pre=None, pre_relu=False, post=None, post_relu=False, n_dev=None):
+    """dense_layer for few live rows (<= ~128: one per cloud) and layers of any width: W is read once for all rows."""
+    x, w = _f(x), _f(w)
+    K, N = w.shape
+    if x.shape[1] != K:
+        raise ValueError("dense_layer_fewrows: input has %d columns, weights expect %d" % (x.shape[1], K))
+    y = torch.empty((x.shape[0], N), dtype=_f32, device=_dev(x))
+    nws = lib.mc_dense_fewrows_workspace_floats(x.shape[0], K, N)
+    ws = torch.empty((nws,), dtype=_f32, device=_dev(x)) if nws else None
+    s1, t1 = (None, None) if pre is None else (_f(pre[0]), _f(pre[1]))
+    s2, t2 = (None, None) if post is None else (_f(post[0]), _f(post[1]))
+    b = None if bias is None else _f(bias)
+    check(lib.mc_dense_layer_fewrows(x.shape[0], _p(n_dev), K, N, _p(x), _p(s1), _p(t1), int(pre_relu), _p(w), _p(b),
+                                     _p(s2), _p(t2), int(post_relu), _p(ws), _p(y), _stream()))
+    return y
+
+
 def split_tf32_transposed(w):
     """(hi, lo) halves of w TRANSPOSED to [N, K] for dense_layer_tc: hi = tf32(w^T), lo = w^T - hi."""
     wt = _f(w).t().contiguous()

@@ -67,6 +67,7 @@ ALGORITHMIC_BYTES = {
                                          4 * sum(int(w.numel()) for w in a[9:15])),
     "scale_shift_act": lambda a, kw, r, B: 8 * _rows(a[0], kw) * a[0].shape[1],
     "dense_layer": lambda a, kw, r, B: _dense_bytes(_rows(a[0], kw), a[1].shape[0], a[1].shape[1]),
+    "dense_layer_fewrows": lambda a, kw, r, B: _dense_bytes(_rows(a[0], kw), a[1].shape[0], a[1].shape[1]),
     "dense_layer_tc": lambda a, kw, r, B: _dense_bytes(_rows(a[0], kw), a[1].shape[1], a[1].shape[0]),
     "mlp_rows": lambda a, kw, r, B: sum(_dense_bytes(_rows(a[0], kw), l[0].shape[0], l[0].shape[1]) for l in a[1]),
 }

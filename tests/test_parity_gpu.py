@@ -379,6 +379,39 @@ def test_dense_glue_matches_torch(env):
     assert torch.equal(part[:10], full[:10])
 
 
+def test_dense_fewrows_matches_torch(env):
+    """mc_dense_layer_fewrows (few rows x wide layer: MCClassH's 2048 -> 1024 -> 512 -> 40 head) against float64
+    torch, 1e-5 relative to the sum of |terms|; capacity rows past the live count are not touched; a second call gives
+    the same bits (the K segments are summed in a fixed order)."""
+    e = env
+    torch, T = e["torch"], e["T"]
+    from mccnn_b200 import ops
+    rng = np.random.default_rng(5)
+    for rows, K, N in ((32, 2048, 1024), (32, 1024, 512), (32, 512, 40), (16, 2048, 1024), (1, 300, 70), (97, 640, 257),
+                       (8, 64, 8), (128, 1664, 64)):
+        x = T(rng.normal(size=(rows, K)).astype(np.float32))
+        w = T((rng.normal(size=(K, N)) / np.sqrt(K)).astype(np.float32))
+        b = T(rng.normal(size=(N,)).astype(np.float32) * 0.1)
+        s1, t1 = T(rng.uniform(0.5, 1.5, K).astype(np.float32)), T(rng.normal(size=K).astype(np.float32) * 0.1)
+        s2, t2 = T(rng.uniform(0.5, 1.5, N).astype(np.float32)), T(rng.normal(size=N).astype(np.float32) * 0.1)
+        a = torch.relu(x.double() * s1.double() + t1.double())
+        want = torch.relu((a @ w.double() + b.double()) * s2.double() + t2.double())
+        scale = (a.abs() @ w.double().abs() + b.double().abs()) * s2.double() + t2.double().abs()
+        got = ops.dense_layer_fewrows(x, w, b, pre=(s1, t1), pre_relu=True, post=(s2, t2), post_relu=True)
+        assert float(((got.double() - want).abs() / scale).max()) <= RTOL, (rows, K, N)
+        assert torch.equal(got, ops.dense_layer_fewrows(x, w, b, pre=(s1, t1), pre_relu=True, post=(s2, t2),
+                                                        post_relu=True))
+        plain = ops.dense_layer_fewrows(x, w)
+        ref = x.double() @ w.double()
+        assert float(((plain.double() - ref).abs() / (x.double().abs() @ w.double().abs() + 1e-30)).max()) <= RTOL
+        # capacity-padded input: only the live rows are computed, with the same bits
+        live = max(1, rows // 2)
+        cnt = torch.tensor([live], dtype=torch.int32, device=e["dev"])
+        xp = torch.cat([x, torch.full((160, K), float("nan"), device=e["dev"])])
+        part = ops.dense_layer_fewrows(xp, w, b, pre=(s1, t1), pre_relu=True, post=(s2, t2), post_relu=True, n_dev=cnt)
+        assert torch.equal(part[:live], got[:live])
+
+
 def test_deferred_batch_norm_is_folded_exactly(env):
     """An inference batch norm (+ ReLU) is returned as a pending affine (runtime.DeferredAffine) and folded into its
     consumer.  The fused scatter (mc_sort_features_affine) equals scale_shift_act followed by sort_features bit for
