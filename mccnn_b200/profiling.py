@@ -8,7 +8,7 @@ ModelNet/ModelNetEval.py:141; this is the per-op view of the same forward).
 Every call of an op of the C-ABI layer (mccnn_b200.ops) is bracketed by a CUDA-event pair on the stream it is issued
 on; its ALGORITHMIC bytes come from SURVEY.md section 8(d)'s per-op formulas evaluated on the LIVE sizes of that call
 (device-side counts are read after the forward, so profiling adds no synchronisation to the timed ops).
-Setting MCCNN_PROFILE=1 makes engine.PlannedForward print such a table for its first planned run.
+bench.py attaches these tables to its JSON line (`kernels`, `other_configs[*].ops`).
 """
 import collections
 

@@ -21,5 +21,12 @@ for tool in memcheck racecheck initcheck synccheck; do
   timeout 600 compute-sanitizer --tool $tool --print-limit 20 python __graft_entry__.py smoke > $out/sanitizer_$tool.log 2>&1
   echo "$tool exit $?" >> $out/sanitizer_$tool.log; tail -3 $out/sanitizer_$tool.log
 done
+echo "== sanitizers over the fuzz sweep and the newest kernels' parity tests (reference kernels excluded)"
+SAN_TESTS="tests/test_fuzz_gpu.py::test_adversarial_geometry_bit_exact tests/test_parity_gpu.py::test_poisson_bit_exact_on_very_ragged_batches tests/test_parity_gpu.py::test_dense_fewrows_matches_torch tests/test_parity_gpu.py::test_find_neighbors_pdf_fused_equals_the_two_ops tests/test_parity_gpu.py::test_find_neighbors_fused_bit_exact"
+for i in 0 1 2 3 4 5 6 7 8 9 10 11; do SAN_TESTS="$SAN_TESTS tests/test_fuzz_gpu.py::test_random_configuration[$i]"; done
+for tool in memcheck racecheck; do
+  MCCNN_NO_REF_KERNELS=1 timeout 1500 compute-sanitizer --tool $tool --print-limit 20 python -m pytest $SAN_TESTS -x -q -m gpu > $out/sanitizer_fuzz_$tool.log 2>&1
+  echo "$tool exit $?" >> $out/sanitizer_fuzz_$tool.log; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|passed|failed" $out/sanitizer_fuzz_$tool.log | tail -3
+done
 fi
 ls -la $out
