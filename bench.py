@@ -258,17 +258,25 @@ def measure_ours(w, args, rank, world, dev, clouds, split, steps, warmup, depth,
     after = None
     if sharded and absolute:
         depth = 1  # the box all-reduce inside the forward uses the default communicator: one forward in flight
-    exs, eps, sync_ex = None, None, None
+    exs, exs_host, eps, sync_ex = None, None, None, None
+    # per-cloud logits (a few KB per sub-0.1-ms step): the device-resident pipeline defers each collect by one step of
+    # its lane (MCCNN_COLLECT=ingraph: collect right behind the put instead)
+    deferred = per_cloud_output(w) and os.environ.get("MCCNN_COLLECT", "deferred") == "deferred"
     if world > 1:
         cap_rows = int(max_over_ranks(rows, world, dev))
         if os.environ.get("MCCNN_GATHER", "peer") == "peer":
             try:
                 exs = [PeerExchange(cap_rows, cols, dev, compact=not per_cloud_output(w)) for _ in range(depth + 1)]
+                if deferred:   # the host-facing pipeline collects inside the step's graph: its own exchanges
+                    exs_host = [PeerExchange(cap_rows, cols, dev, compact=False) for _ in range(depth)]
                 sync_ex = PeerExchange(1, 4, dev)
                 gather_mode = ("all_gather of the %s logits over NVLink peer memory (symmetric ring buffers, peer stores + "
                                "flags; csrc/peer_gather.cu): put = last node of each lane's CUDA graph, collect %s, "
                                "overflow flags gathered with the rows" %
                                ("per-cloud" if per_cloud_output(w) else "per-point (unequal row counts, compacted)",
+                                ("of step k captured in front of the put of the lane's step k + 1 and flushed behind the "
+                                 "last step inside the timed region (no forward waits on a peer; the host-facing e2e "
+                                 "pipeline collects inside the step's own graph)") if deferred else
                                 "right behind it in the graph" if per_cloud_output(w) else "on a side stream"))
             except Exception as exc:  # noqa: BLE001
                 sys.stderr.write("bench: peer-memory exchange unavailable (%r); using NCCL\n" % (exc,))
@@ -327,9 +335,15 @@ def measure_ours(w, args, rank, world, dev, clouds, split, steps, warmup, depth,
     pipe_res = [pack_batch(*r) for r in resident]
     for i in range(n_batches, n_pipe):
         pipe_res.append(pack_batch(*(torch.from_numpy(a).to(dev) for a in make(i))))
+    defer = deferred and exs is not None
     pipe = PipelinedForward(fn, rows, depth=depth, slack=1.3, epilogues=None if eps is None else eps[:depth],
-                            exchanges=None if exs is None else exs[:depth], collect_in_graph=in_graph)
+                            exchanges=None if exs is None else exs[:depth], collect_in_graph=in_graph and not defer,
+                            collect_deferred=defer)
     pipe.calibrate(resident)
+    pipe_host = pipe
+    if defer:
+        pipe_host = PipelinedForward(fn, rows, depth=depth, slack=1.3, exchanges=exs_host, collect_in_graph=True)
+        pipe_host.calibrate(resident)
     for i in range(warm * depth):
         pipe.submit_packed(pipe_res[i % n_pipe], after=after)
     pipe.join()
@@ -404,7 +418,7 @@ def measure_ours(w, args, rank, world, dev, clouds, split, steps, warmup, depth,
     for i in range(e2e_steps):
         hf.call_packed(pinned_blocks[i % n_batches])
     res["e2e_latency_s"] = max_over_ranks((time.perf_counter() - t0) / e2e_steps, world, dev)
-    phf = PipelinedHostForward(pipe, dev)
+    phf = PipelinedHostForward(pipe_host, dev)
     after_h = (lambda out: after(out, None)) if after is not None else None   # the host gets ALL logits
     for rep in range(2):
         warm_t = [phf.submit_packed(pinned_blocks[i % n_batches], after=after_h) for i in range(depth)]

@@ -234,7 +234,9 @@ int mc_allgather_rows_p2p(int floatsPerRank, int rank, int worldSize, const floa
  * waits only for the acknowledgement of step seq - slots; mc_peer_collect -- on the stream that feeds the host copy --
  * waits for every rank's put of the step, copies the rows out (padded or compacted in rank order: per-point logits of
  * unequal length), reports per-rank (rows, flag), the total and the MAX flag in `meta`, and acknowledges.  Ranks may
- * drift apart by `slots` steps before anything blocks.  state: 4 device ints, zero before the first step. */
+ * drift apart by `slots` steps before anything blocks.  state: 4 device ints, zero before the first step.
+ * compact: bit 0 = rows of all ranks contiguous in rank order; bit 1 = do nothing unless a put is still uncollected
+ * (the deferred collect captured in front of a lane's next put, and the flush behind its last step). */
 long long mc_peer_exchange_buffer_floats(int capRows, int cols, int worldSize, int slots);
 int mc_peer_put(int capRows, const int* dRows, int cols, int rank, int worldSize, int slots, const float* local,
                 const int* dFlag, const long long* peerBufPtrs, int* state, void* stream);

@@ -102,6 +102,10 @@ __global__ void __launch_bounds__(256) peer_collect_kernel(PeerLayout L, int ran
                                                            float* __restrict__ out, int* __restrict__ meta) {
     __shared__ int sLast;
     __shared__ int sRows[256], sBase[257];
+    // bit 1 of `compact`: collect only if a put is outstanding (the deferred collect at the head of a lane's next step
+    // and the flush behind its last one share one call); state[0] / state[1] only change in stream order with this kernel
+    if ((compact & 2) && state[1] >= state[0]) return;
+    compact &= 1;
     const int seq = state[1] + 1;
     const int slot = seq % L.slots;
     const float* mine = reinterpret_cast<const float*>(peerBufs[rank]);
@@ -263,6 +267,7 @@ extern "C" int mc_peer_put(int capRows, const int* dRows, int cols, int rank, in
 // Step state[1] + 1: waits for every rank's put of that step, copies the rows out of the local buffer -- padded (rank
 // r's rows at r * capRows) or, compact != 0, contiguous in rank order -- fills meta (2 ints (rows, flag) per rank, then
 // the total row count and the MAX of the flags; may be NULL) and acknowledges the step to every rank.
+// compact: bit 0 = compacted output, bit 1 = do nothing unless a put of this exchange is still uncollected.
 extern "C" int mc_peer_collect(int capRows, int cols, int rank, int worldSize, int slots, int compact,
                                const long long* peerBufPtrs, int* state, float* out, int* meta, void* stream) {
     MC_REQUIRE(capRows > 0 && cols > 0 && worldSize > 0 && worldSize <= 256 && rank >= 0 && rank < worldSize && slots >= 2,

@@ -60,7 +60,7 @@ def pack_batch(pts, bids, feats, pin=False):
 
 class PlannedForward:
     def __init__(self, fn, out_rows, use_graph=True, slack=1.3, multistream=True, epilogue=None, exchange=None,
-                 collect_in_graph=False):
+                 collect_in_graph=False, collect_deferred=False):
         """fn(points, batchIds, features) -> [>= out_rows, F] tensor; out_rows rows of it are the result.
         multistream: overlap the hierarchy / convolution-geometry / feature chains on three streams (runtime.planned).
         epilogue(result) -> tensor: applied to the out_rows result rows in every mode and CAPTURED INTO THE GRAPH with
@@ -71,11 +71,18 @@ class PlannedForward:
         stream never waits on a peer -- and leaves (rows of all ranks, meta) in `self.gathered`.
         collect_in_graph: capture the collect right behind the put instead (one graph launch per step and nothing else
         on the host: the better trade for the few-KB per-cloud logits of a sub-0.1-ms step; the side-stream collect is
-        for per-point logits of multi-ms steps)."""
+        for per-point logits of multi-ms steps).
+        collect_deferred: the collect of step k is issued right before the put of step k + 1 (same graph, same single
+        host launch) and by flush() behind the last step: by then every peer's put of step k has long landed, so no
+        forward ever waits on a peer -- ranks only couple through the exchange's ring of slots (4 steps of drift).
+        `gathered` then holds step k's rows after the lane's next step or flush()."""
         self.fn = fn
         self.epilogue = epilogue
         self.exchange = exchange
         self.collect_in_graph = bool(collect_in_graph)
+        self.collect_deferred = bool(collect_deferred)
+        if self.collect_in_graph and self.collect_deferred:
+            raise ValueError("PlannedForward: collect_in_graph and collect_deferred exclude each other")
         self.collect_stream = None
         self.gathered = None
         self.multistream = multistream
@@ -109,6 +116,8 @@ class PlannedForward:
         if self.exchange is not None:
             res = res.contiguous()
             flag = self.plan.overflow if (self.plan is not None and _rt.mode() != "exact") else None
+            if self.collect_deferred:
+                self.gathered = self.exchange.collect(pending_only=True)   # the previous step's rows
             self.exchange.put(res, flag=flag)
             if self.collect_in_graph:
                 self.gathered = self.exchange.collect()
@@ -116,7 +125,7 @@ class PlannedForward:
 
     def _collect(self):
         """The collect that matches the put just enqueued (every put needs one on every rank)."""
-        if self.exchange is None or self.collect_in_graph:
+        if self.exchange is None or self.collect_in_graph or self.collect_deferred:
             return
         cs = self.collect_stream
         if cs is None:
@@ -125,6 +134,12 @@ class PlannedForward:
         cs.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(cs):
             self.gathered = self.exchange.collect()
+
+    def flush(self):
+        """collect_deferred: collect the last step's rows (waits for every rank's put of it) on the current stream."""
+        if self.exchange is not None and self.collect_deferred:
+            self.gathered = self.exchange.collect(pending_only=True)
+        return self.gathered
 
     def _planned(self, pts, bids, feats):
         with _rt.planned(self.plan, pts.device, multistream=self.multistream):
@@ -145,7 +160,7 @@ class PlannedForward:
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):  # warm-up outside capture (allocator, lazy module loading, NCCL communicator)
             self._planned_finish(*self._static_in)
-            if self.exchange is not None and not self.collect_in_graph:
+            if self.exchange is not None and not self.collect_in_graph and not self.collect_deferred:
                 self.exchange.collect()
         torch.cuda.current_stream().wait_stream(side)
         g = torch.cuda.CUDAGraph()
@@ -291,7 +306,7 @@ class PipelinedForward:
     (out, overflow_flag) device tensors, valid until the lane is reused."""
 
     def __init__(self, fn, out_rows, depth=4, slack=1.3, multistream=True, epilogues=None, exchanges=None,
-                 collect_in_graph=False):
+                 collect_in_graph=False, collect_deferred=False):
         """epilogues: one callable per lane (see PlannedForward).  Lanes run concurrently, so collectives in them must
         use ONE PROCESS GROUP PER LANE: an NCCL communicator may not be driven from two streams at once.
         exchanges: one PeerExchange per lane: the step's put is the last node of the lane's graph, its collect runs on
@@ -300,7 +315,7 @@ class PipelinedForward:
         self.engines = [PlannedForward(fn, out_rows, use_graph=True, slack=slack, multistream=multistream,
                                        epilogue=None if epilogues is None else epilogues[i],
                                        exchange=None if exchanges is None else exchanges[i],
-                                       collect_in_graph=collect_in_graph)
+                                       collect_in_graph=collect_in_graph, collect_deferred=collect_deferred)
                         for i in range(depth)]
         self.streams = None
         self._events = [None] * depth
@@ -317,7 +332,7 @@ class PipelinedForward:
         dev = batches[0][0].device
         self.streams = [torch.cuda.Stream(device=dev) for _ in range(self.depth)]
         for e in self.engines:
-            if e.exchange is not None and not e.collect_in_graph:
+            if e.exchange is not None and not e.collect_in_graph and not e.collect_deferred:
                 e.collect_stream = torch.cuda.Stream(device=dev)
         for e, s in zip(self.engines, self.streams):  # capture every lane's graph up front
             s.wait_stream(torch.cuda.current_stream(dev))
@@ -366,6 +381,14 @@ class PipelinedForward:
         return self.engines[ticket].gathered
 
     def join(self):
+        """The caller's stream waits for every lane; deferred collects are flushed first (every put is collected)."""
+        for lane, e in enumerate(self.engines):
+            if e.exchange is not None and e.collect_deferred and self._events[lane] is not None:
+                with torch.cuda.stream(self.streams[lane]):
+                    e.flush()
+                    ev = torch.cuda.Event()
+                    ev.record(self.streams[lane])
+                self._events[lane] = ev
         for ev in self._events:
             if ev is not None:
                 torch.cuda.current_stream().wait_event(ev)
@@ -400,6 +423,7 @@ class PipelinedHostForward:
         self._has_extra[lane] = None
         with torch.cuda.stream(s):
             eng.run_packed(pinned_block)                                   # one H2D + one graph launch (+ collect)
+            eng.flush()                                                    # deferred collect: the host wants THIS step
             last = s
             if eng.exchange is not None:                # ONE D2H: rows of all ranks + (rows, flag) of every rank
                 last = eng.collect_stream if eng.collect_stream is not None else s
@@ -582,10 +606,12 @@ class PeerExchange:
             n_dev = torch.full((1,), rows.shape[0], dtype=torch.int32, device=rows.device)
         ops.peer_put(rows, self.ptrs, self.state, self.rank, self.world, self.slots, self.cap_rows, n_dev, flag)
 
-    def collect(self):
+    def collect(self, pending_only=False):
+        """pending_only: a no-op unless a put of this exchange is still uncollected (decided on the device, so the call
+        can sit in a CUDA graph that runs both as a lane's first step and as a later one)."""
         from . import ops
         return ops.peer_collect(self.ptrs, self.state, self.rank, self.world, self.slots, self.cap_rows, self.cols,
-                                self.out, self.meta, self.compact)
+                                self.out, self.meta, self.compact, pending_only=pending_only)
 
     def __call__(self, rows):
         """put + collect back to back on the current stream (gathered rows inside the same graph)."""

@@ -424,7 +424,9 @@ def peer_put(local, peer_ptrs, state, rank, world, slots, cap_rows, n_dev=None, 
                           _p(flag), _p(peer_ptrs), _p(state), _stream()))
 
 
-def peer_collect(peer_ptrs, state, rank, world, slots, cap_rows, cols, out, meta, compact):
-    check(lib.mc_peer_collect(int(cap_rows), int(cols), int(rank), int(world), int(slots), int(bool(compact)),
+def peer_collect(peer_ptrs, state, rank, world, slots, cap_rows, cols, out, meta, compact, pending_only=False):
+    """pending_only: do nothing unless a put of this exchange is still uncollected (decided on the device)."""
+    check(lib.mc_peer_collect(int(cap_rows), int(cols), int(rank), int(world), int(slots),
+                              int(bool(compact)) | (2 if pending_only else 0),
                               _p(peer_ptrs), _p(state), _p(out), _p(meta), _stream()))
     return out, meta

@@ -295,6 +295,48 @@ def test_peer_gather_single_rank_group():
             xs.fill_(float(step))
             g2.replay()
             assert torch.equal(px.collect()[0], xs)
+        # deferred collect (pending_only): a no-op when nothing is outstanding, otherwise the previous step's rows --
+        # captured in front of the put, so that a lane's graph never waits on a peer's put of the SAME step
+        pd = PeerExchange(8, 40, dev)
+        before = pd.out.clone()
+        pd.collect(pending_only=True)
+        assert torch.equal(pd.out, before) and int(pd.state[1]) == 0        # nothing was outstanding
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            pd.collect(pending_only=True)
+            pd.put(xs)
+        torch.cuda.current_stream().wait_stream(side)
+        g3 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g3):
+            pd.collect(pending_only=True)
+            pd.put(xs)
+        prev = xs.clone()                                                     # rows of the warm-up put
+        for step in range(9):
+            xs.fill_(float(100 + step))
+            g3.replay()
+            assert torch.equal(pd.out, prev)                                  # step k's graph delivers step k - 1
+            prev = xs.clone()
+        pd.collect(pending_only=True)                                         # flush
+        assert torch.equal(pd.out, prev)
+        pd.collect(pending_only=True)
+        assert int(pd.state[0]) == int(pd.state[1]) == 10
+        # the same through the engine: PipelinedForward(collect_deferred=True) -- join() flushes every lane
+        from mccnn_b200.engine import PipelinedForward
+        B = 4
+        fn, store = _make(B, 16, 40, dev)
+        pts, bids, feats = make_batch(B, 512, "sphere", seed=41)
+        batch = tuple(torch.from_numpy(a).to(dev) for a in (pts, bids, feats))
+        want = fn(*batch)[:B].clone()
+        lanes = [PeerExchange(B, 40, dev) for _ in range(2)]
+        pipe = PipelinedForward(fn, B, depth=2, exchanges=lanes, collect_deferred=True)
+        pipe.calibrate([batch])
+        for i in range(5):
+            pipe.submit(*batch)
+        pipe.join()
+        torch.cuda.synchronize()
+        for ex in lanes:
+            assert int(ex.state[0]) == int(ex.state[1])                       # every put was collected
+            assert torch.equal(ex.out, want)
     finally:
         if created:
             dist.destroy_process_group()

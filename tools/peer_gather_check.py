@@ -52,7 +52,7 @@ def main():
         m = meta.cpu()
         ok &= int(m[2 * world]) == world * rows and int(m[2 * world + 1]) == (1 if step == 17 else 0)
     # unequal row counts, compacted (per-point logits of a segmentation shard)
-    cap = 5000
+    cap = 1000 + 731 * world + 600     # the largest shard below: 1000 + 731 * (world - 1) + 97 * 5
     pc = PeerExchange(cap, 21, dev, compact=True)
     for step in range(6):
         n = 1000 + 731 * rank + 97 * step

@@ -1,3 +1,5 @@
 #!/bin/bash
-timeout 600 python -m pytest tests/test_parity_gpu.py -x -q -m gpu -k "persistent_conv" 2>&1 | tail -3
-bash tools/gpu_multi.sh 2 r2final_n2 quick
+bash tools/gpu_multi.sh 8 r2final2_n8 bench
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29533"
+MCCNN_COLLECT=ingraph timeout 300 $TR bench.py --gpus 8 --steps 20 --warmup 5 --no-other-configs 2>/dev/null > gpurun_out/r2final2_n8/bench_n8_s20_ingraph.json; cut -c1-260 gpurun_out/r2final2_n8/bench_n8_s20_ingraph.json
+timeout 300 $TR bench.py --gpus 8 --steps 20 --warmup 5 --no-other-configs 2>/dev/null > gpurun_out/r2final2_n8/bench_n8_s20_b.json; cut -c1-260 gpurun_out/r2final2_n8/bench_n8_s20_b.json
