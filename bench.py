@@ -259,9 +259,10 @@ def measure_ours(w, args, rank, world, dev, clouds, split, steps, warmup, depth,
     if sharded and absolute:
         depth = 1  # the box all-reduce inside the forward uses the default communicator: one forward in flight
     exs, exs_host, eps, sync_ex = None, None, None, None
-    # per-cloud logits (a few KB per sub-0.1-ms step): the device-resident pipeline defers each collect by one step of
-    # its lane (MCCNN_COLLECT=ingraph: collect right behind the put instead)
-    deferred = per_cloud_output(w) and os.environ.get("MCCNN_COLLECT", "deferred") == "deferred"
+    # per-cloud logits (a few KB per sub-0.1-ms step): collect captured right behind the put.  MCCNN_COLLECT=deferred:
+    # the device-resident pipeline collects step k in front of the lane's put k + 1 instead (no forward waits on a
+    # peer); measured no faster on 2 and 8 GPUs (profiles/r2_multi_gpu.md), so not the default
+    deferred = per_cloud_output(w) and os.environ.get("MCCNN_COLLECT", "ingraph") == "deferred"
     if world > 1:
         cap_rows = int(max_over_ranks(rows, world, dev))
         if os.environ.get("MCCNN_GATHER", "peer") == "peer":
@@ -555,6 +556,9 @@ def run_config1(args, dev, arm):
     ms = []
     for _ in range(steps):
         flush_l2(flush)
+        # keep the GPU busy (~0.2 ms) while the host gets through the op's Python wrapper: the events then bracket the
+        # kernels, not the host's enqueue latency (which `e2e` below measures)
+        torch.cuda._sleep(400_000)
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         X.spatial_conv(*res, *attrs)
