@@ -100,6 +100,7 @@ _TC_MIN_ROWS = 129
 _TC_MIN_MACS = 1 << 26
 # few rows (one per cloud) against a wide layer: the layer is a stream of W -- dense.cu's few-rows kernel reads it once
 _FEWROWS_MAX_ROWS = 128
+_FEWROWS_MAX_CAPACITY = 1024     # rows of the (capacity-padded) input: bounds the K-segment workspace
 _FEWROWS_MIN_WEIGHTS = 1 << 16
 
 
@@ -109,7 +110,8 @@ def _layer(x, w, b, pre, pre_relu, post, post_relu, nd, h):
             ops.dense_layer_tc_supported(w.shape[0], w.shape[1])):
         hi, lo = _split_weights(w)
         return ops.dense_layer_tc(x, hi, lo, b, pre=pre, pre_relu=pre_relu, post=post, post_relu=post_relu, n_dev=nd)
-    if rows <= _FEWROWS_MAX_ROWS and w.shape[0] * w.shape[1] >= _FEWROWS_MIN_WEIGHTS:
+    if (rows <= _FEWROWS_MAX_ROWS and x.shape[0] <= _FEWROWS_MAX_CAPACITY and
+            w.shape[0] * w.shape[1] >= _FEWROWS_MIN_WEIGHTS):
         return ops.dense_layer_fewrows(x, w, b, pre=pre, pre_relu=pre_relu, post=post, post_relu=post_relu, n_dev=nd)
     return ops.dense_layer(x, w, b, pre=pre, pre_relu=pre_relu, post=post, post_relu=post_relu, n_dev=nd, rows_hint=h)
 
