@@ -6,6 +6,9 @@ Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl refere
   oracle.numpy_ops  vectorised NumPy restatement of compute_pdf / spatial_conv (BASELINE.json config 1)
   oracle.ref      torch-CUDA bindings of oracle/_ref/libmccnn_ref.so = the reference's own kernels (GPU box only)
   oracle.pipeline MCClassS forward assembled from oracle.cpu ops (+ NumPy dense glue)
+  oracle.ref_nets the reference's builder and the four benchmarked topologies restated over an op module (oracle.ref on
+                  the GPU = bench.py --impl reference; oracle.cpu behind torch CPU tensors = cpu_baseline), held to the
+                  outputs of the reference's unchanged model files (oracle.ref_models, tests/golden/model_*.npz)
 """
 import os
 import subprocess
