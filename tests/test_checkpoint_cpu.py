@@ -29,6 +29,16 @@ def test_crc32c_chunked_path_equals_the_byte_loop(n):
     assert ck.crc32c(data) == ck._crc32c_scalar(data)
 
 
+def test_crc32c_and_mask_equal_tensorboards_implementation():
+    """tensorboard ships an independent pure-Python CRC32C + the LevelDB / TFRecord mask (compat/tensorflow_stub)."""
+    tb = pytest.importorskip("tensorboard.compat.tensorflow_stub.pywrap_tensorflow")
+    rng = np.random.default_rng(4)
+    for n in (0, 1, 7, 1000, 70_001):
+        data = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        assert ck.crc32c(data) == tb.crc32c(data)
+        assert ck._mask(ck.crc32c(data)) == tb.masked_crc32c(data)
+
+
 def test_snappy_decoder():
     # literal "abcd", then a copy of 8 bytes from offset 4 (overlapping its own output), then literal "xy"
     raw = bytes([14]) + bytes([3 << 2]) + b"abcd" + bytes([((8 - 4) << 2) | 1, 4]) + bytes([1 << 2]) + b"xy"
